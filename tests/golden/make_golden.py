@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Mint the golden vectors under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py [--only rollout,step,grid,env,data]
+
+The reference has no tests and no golden vectors of its own, so parity is pinned
+on outputs of the reference itself, generated here through oracle/ref_harness.py (stubs for the
+plotting / pygame / casadi imports; nothing in the reference is modified).  Every file written here
+is an input/output pair of a reference function that tests/ replays against the oracle restatement
+(CPU, `-m "not gpu"`) and against the CUDA path (`-m gpu`).
+
+Also exports the trained C3M controller weights (data/trained_controller/controller_CAR_3layers.pth.tar,
+loaded by systems/sytem_CAR.py:113-125) to density_planner_b200/data/controller_CAR_3layers.npz so the
+GPU box (which has no /root/reference) can run the real controller.
+"""
+import argparse
+import io
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_harness as rh  # noqa: E402
+
+torch.set_num_threads(1)  # single-thread BLAS: reproducible summation order for the goldens
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v))
+                                 for k, v in arrs.items()})
+    print("wrote %s (%.1f KB)" % (name, os.path.getsize(path) / 1e3))
+
+
+def export_weights(car):
+    sd = car.controller.controller.state_dict()
+    out = os.path.join(ROOT, "density_planner_b200", "data")
+    os.makedirs(out, exist_ok=True)
+    np.savez(os.path.join(out, "controller_CAR_3layers.npz"), **{k: v.numpy() for k, v in sd.items()})
+    print("exported controller weights:", {k: tuple(v.shape) for k, v in sd.items()})
+
+
+def u_raw_traj(car, x_traj, xref_traj, uref_traj):
+    """Unclipped controller output along a stored trajectory (for the clip-flip audit)."""
+    ctrl = car.controller
+    out = torch.zeros(x_traj.shape[0], 2, uref_traj.shape[2])
+    with torch.no_grad():
+        for i in range(uref_traj.shape[2]):
+            x = x_traj[:, :, [i]]
+            xe = x[:, :4, :] - xref_traj[:, :4, [i]]
+            xe[:, 2, :] += x[:, 4, :]
+            out[:, :, [i]] = ctrl.controller(x[:, :4, :], xe, uref_traj[:, :, [i]])
+    return out
+
+
+def gen_rollout(car, args):
+    # (1) config-1 shape: seed 0, get_valid_ref + sample_xe0(20), full horizon
+    torch.manual_seed(0)
+    with rh.ref_cwd():
+        up, uref, xref = car.get_valid_ref(args)
+        xe0 = car.sample_xe0(20)
+        xe, rl = car.compute_density(xe0.clone(), xref, uref, args.dt_sim, cutting=True, log_density=True)
+        ur = u_raw_traj(car, xe + xref, xref, uref)
+    margin = (ur.abs() - 3).abs().amin(dim=(1, 2))
+    save("rollout_cfg1.npz", xe0=xe0[:, :, 0], xref=xref[0], uref=uref[0], up=up, dt=np.float32(args.dt_sim),
+         xe_traj=xe, rholog_traj=rl[:, 0, :], clip_margin=margin)
+
+    # (2) N=2000,T=300 and N=4000,T=100 on other references; stored every 10th step
+    for name, seed, N, T in (("rollout_n2000_t300", 1, 2000, 300), ("rollout_n4000_t100", 2, 4000, 100)):
+        torch.manual_seed(seed)
+        with rh.ref_cwd():
+            up, uref, xref = car.get_valid_ref(args)
+            uref, xref = uref[:, :, :T], xref[:, :, :T + 1]
+            xe0 = car.sample_xe0(N)
+            xe, rl = car.compute_density(xe0.clone(), xref, uref, args.dt_sim, cutting=True, log_density=True)
+            ur = u_raw_traj(car, xe + xref, xref, uref)
+        margin = (ur.abs() - 3).abs().amin(dim=(1, 2))
+        clipped = (ur.abs() > 3).any(dim=1).float().mean().item()
+        print(name, "fraction of (sample,step) with a clipped input: %.3f" % clipped)
+        save(name + ".npz", xe0=xe0[:, :, 0], xref=xref[0], uref=uref[0], dt=np.float32(args.dt_sim),
+             xe_traj=xe[:, :, ::10], rholog_traj=rl[:, 0, ::10], clip_margin=margin, stride=10)
+
+    # (3) non-log density + rho0 given + no cutting (planner LE call shape, short)
+    torch.manual_seed(3)
+    with rh.ref_cwd():
+        up, uref, xref = car.get_valid_ref(args)
+        uref, xref = uref[:, :, :150], xref[:, :, :151]
+        xe0 = car.sample_xe0(256)
+        rho0 = torch.rand(256, 1, 1) + 0.5
+        xe_a, rho_a = car.compute_density(xe0.clone(), xref, uref, args.dt_sim, rho0=rho0.clone(), cutting=True,
+                                          log_density=False)
+        xe_b, rho_b = car.compute_density(xe0.clone(), xref, uref, args.dt_sim, cutting=False, log_density=True,
+                                          compute_density=True)
+        xe_c, rho_c = car.compute_density(xe0.clone(), xref, uref, args.dt_sim, compute_density=False)
+    assert rho_c is None
+    save("rollout_modes.npz", xe0=xe0[:, :, 0], xref=xref[0], uref=uref[0], rho0=rho0[:, 0, 0],
+         dt=np.float32(args.dt_sim), xe_lin=xe_a[:, :, ::5], rho_lin=rho_a[:, 0, ::5], xe_log=xe_b[:, :, ::5],
+         rholog=rho_b[:, 0, ::5], xe_nodens=xe_c[:, :, ::5], stride=5)
+
+
+def gen_step(car, args):
+    """Single-step API on 4096 samples, incl. samples that straddle the +-3 clip boundary."""
+    torch.manual_seed(4)
+    N = 4096
+    xref = torch.tensor([1.0, -2.0, 0.7, 4.0, 0.0]).reshape(1, 5, 1)
+    with rh.ref_cwd():
+        xe = torch.cat((car.sample_xe0(N // 2), car.sample_xe(N // 2)), 0)  # half/full error range: clipped and unclipped
+    x = xe + xref
+    uref = torch.tensor([0.8, -1.1]).reshape(1, 2, 1)
+    with rh.ref_cwd():
+        u = car.u_func(x, xref, uref)
+        f = car.f_func(x, xref, uref)
+        dudx = car.dudx_func(x.clone(), xref, uref).detach()
+        dfdx = car.dfdx_func(x.clone(), xref, uref).detach()
+        div = car.divf_func(x.clone(), xref, uref).detach()
+        xn = car.get_next_x(x, xref, uref, args.dt_sim)
+        rho = torch.rand(N) + 0.5
+        rn = car.get_next_rho(x.clone(), xref, uref, rho, args.dt_sim).detach()
+        rln = car.get_next_rholog(x.clone(), xref, uref, rho, args.dt_sim).detach()
+        xe_c = x[:, :4, :] - xref[:, :4, :]
+        xe_c[:, 2, :] += x[:, 4, :]
+        uraw = car.controller.controller(x[:, :4, :], xe_c, uref).detach()
+    print("step: clipped fraction u0 %.3f u1 %.3f" % ((uraw[:, 0].abs() > 3).float().mean(),
+                                                       (uraw[:, 1].abs() > 3).float().mean()))
+    save("step_api.npz", x=x[:, :, 0], xref=xref[0, :, 0], uref=uref[0, :, 0], dt=np.float32(args.dt_sim),
+         u=u[:, :, 0], u_raw=uraw[:, :, 0], f=f[:, :, 0], dudx=dudx, dfdx=dfdx, div=div, x_next=xn[:, :, 0],
+         rho=rho, rho_next=rn, rholog_next=rln)
+
+
+def grid_inputs(n, seed):
+    """Deterministic world positions; tests regenerate them with the same RandomState call sequence."""
+    rs = np.random.RandomState(seed)
+    px = rs.uniform(-13.0, 13.0, n).astype(np.float32)
+    py = rs.uniform(-31.0, 11.0, n).astype(np.float32)
+    return px, py
+
+
+def gen_grid(car, args):
+    rh.install()
+    with rh.ref_cwd():
+        from motion_planning.utils import pos2gridpos, gridpos2pos, pred2grid
+        from systems.utils import get_density_map
+    n = 400000
+    px, py = grid_inputs(n, 11)
+    # exact half-cell points and cell centres
+    hx = (np.arange(-2, 484, dtype=np.float32) * np.float32(0.05) + np.float32(-12.0)).astype(np.float32)
+    hy = (np.arange(-2, 804, dtype=np.float32) * np.float32(0.05) + np.float32(-30.0)).astype(np.float32)
+    gx, gy = pos2gridpos(args, pos_x=torch.from_numpy(px), pos_y=torch.from_numpy(py))
+    ghx, _ = pos2gridpos(args, pos_x=torch.from_numpy(hx))
+    _, ghy = pos2gridpos(args, pos_y=torch.from_numpy(hy))
+    # inverse map on float grid positions
+    rs = np.random.RandomState(12)
+    fgx = rs.uniform(-50, 300, 4096).astype(np.float32)
+    fgy = rs.uniform(-50, 450, 4096).astype(np.float32)
+    bx, by = gridpos2pos(args, pos_x=torch.from_numpy(fgx), pos_y=torch.from_numpy(fgy))
+    save("pos2gridpos.npz", n=n, seed=11, gx=gx.numpy().astype(np.int16), gy=gy.numpy().astype(np.int16),
+         hx=hx, hy=hy, ghx=ghx.numpy().astype(np.int16), ghy=ghy.numpy().astype(np.int16),
+         fgx=fgx, fgy=fgy, bx=bx, by=by)
+
+    # pred2grid: 10k samples around a point, rho positive
+    rs = np.random.RandomState(13)
+    N = 10000
+    x = np.zeros((N, 5, 1), np.float32)
+    x[:, 0, 0] = rs.normal(1.3, 0.8, N)
+    x[:, 1, 0] = rs.normal(-12.0, 1.5, N)
+    # some beyond the LOW grid edge (clamped to cell 0, utils.py:261-262).  Beyond the HIGH edge the reference
+    # clamps to G (not G-1) and then fails on the slice assignment at :277, so that case has no golden.
+    x[:50, 0, 0] = rs.uniform(-13.0, -11.5, 50)
+    x[50:100, 1, 0] = rs.uniform(-31.0, -29.5, 50)
+    rho = rs.uniform(0.0, 1.0, (N, 1, 1)).astype(np.float32)
+    grid, gridpos = pred2grid(torch.from_numpy(x), torch.from_numpy(rho), args, return_gridpos=True)
+    nz = grid[:, :, 0].nonzero()
+    save("pred2grid.npz", x=x[:, :2, 0], rho=rho[:, 0, 0], nz=nz.numpy().astype(np.int16),
+         val=grid[nz[:, 0], nz[:, 1], 0], gridpos=gridpos.numpy().astype(np.int16), shape=np.array(grid.shape))
+
+    # get_density_map: error-state histogram, log density
+    rs = np.random.RandomState(14)
+    N = 20000
+    xe = rs.normal(0, 0.6, (N, 2)).astype(np.float32)
+    rl = rs.normal(0, 3.0, N).astype(np.float32)
+    dm, rb = get_density_map(torch.from_numpy(xe.copy()), torch.from_numpy(rl.copy()), args, log_density=True,
+                             type="LE", system=car)
+    dm_lin, _ = get_density_map(torch.from_numpy(xe.copy()), torch.from_numpy(np.exp(rl)), args, log_density=False,
+                                type="LE", system=car)
+    dm_mc, _ = get_density_map(torch.from_numpy(xe.copy()), torch.ones(N), args, log_density=False, type="MC",
+                               system=car)
+    save("density_map.npz", xe=xe, rholog=rl, dm=dm, range_bins=np.array([[float(a), float(b)] for a, b in rb]),
+         dm_lin=dm_lin, dm_mc=dm_mc)
+
+
+def synth_samples(seed, N, Ts, xy_ref):
+    """Synthetic weighted sample set around a reference path (numpy RandomState: reproducible in tests)."""
+    rs = np.random.RandomState(1000 + seed)
+    idx = rs.randint(0, xy_ref.shape[0], N)
+    xy = xy_ref[idx] + (0.3 * rs.standard_normal((N, 2, Ts))).astype(np.float32)
+    rho = rs.uniform(0, 1, (N, Ts)).astype(np.float32)
+    rho /= rho.sum(axis=0, keepdims=True)
+    return xy.astype(np.float32), rho.astype(np.float32)
+
+
+def gen_env(car, args, seeds):
+    rh.install()
+    with rh.ref_cwd():
+        from motion_planning.example_objects import create_mp_task
+        from motion_planning.MotionPlannerGrad import MotionPlannerGrad
+    os.makedirs("/tmp/dp_log", exist_ok=True)
+    for seed in seeds:
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        with rh.ref_cwd():
+            ego = create_mp_task(args, seed)
+            planner = MotionPlannerGrad(ego, path_log="/tmp/dp_log/")
+        env = ego.env
+        out = dict(grid=env.grid.numpy(), seed=seed)
+        # sparse check values of the gradient grids (the oracle rebuilds them from `grid`)
+        rs = np.random.RandomState(77 + seed)
+        ci = np.stack([rs.randint(0, 241, 20000), rs.randint(0, 401, 20000), rs.randint(0, 101, 20000)], 1)
+        out["chk_idx"] = ci.astype(np.int16)
+        out["chk_gx"] = env.grid_gradientX.numpy()[ci[:, 0], ci[:, 1], ci[:, 2]]
+        out["chk_gy"] = env.grid_gradientY.numpy()[ci[:, 0], ci[:, 1], ci[:, 2]]
+        out["gx_sum"] = np.float64(env.grid_gradientX.double().sum())
+        out["gy_sum"] = np.float64(env.grid_gradientY.double().sum())
+
+        # LE sample set (the planner's own call): seed 0 and 1 only (8 s each)
+        if seed < 2:
+            up = 0.5 * torch.randn(1, 2, 10)
+            with rh.ref_cwd():
+                uref_traj, xref_traj, x_traj, rho_traj = planner.get_traj(up, compute_density=True, use_nn=False,
+                                                                         plot=False)
+            x_le = x_traj.clone().requires_grad_(True)
+            r_le = rho_traj.clone().requires_grad_(True)
+            c = planner.get_cost_coll(x_le, r_le)
+            c.sum().backward()
+            cmax = planner.get_cost_coll(x_traj, rho_traj, get_max=True)
+            out.update(le_up=up, le_xe0=ego.xe0[:, :, 0], le_rho0=ego.rho0[:, 0, 0], le_xref0=ego.xref0[0, :, 0],
+                       le_x=x_traj[:, :2, :], le_rho=rho_traj[:, 0, :], le_cost=c.detach(), le_cost_max=cmax,
+                       le_gx=x_le.grad[:, :2, :], le_grho=r_le.grad[:, 0, :101])
+            ci_ = planner.get_cost_coll_initialize(x_traj[:100])
+            out["le_cost_init"] = ci_
+
+        # synthetic weighted samples around a straight reference through the street
+        Ts = 101
+        tt = np.linspace(0, 1, Ts, dtype=np.float32)
+        path = np.stack([0.5 * np.sin(3 * tt), -28 + 36 * tt], 0)[None].astype(np.float32)  # (1,2,Ts)
+        xy, rho = synth_samples(seed, 20000, Ts, path)
+        x5 = torch.zeros(xy.shape[0], 5, Ts)
+        x5[:, :2, :] = torch.from_numpy(xy)
+        x5.requires_grad_(True)
+        r = torch.from_numpy(rho).unsqueeze(1).clone().requires_grad_(True)
+        c = planner.get_cost_coll(x5, r)
+        c.sum().backward()
+        cmax = planner.get_cost_coll(x5.detach(), r.detach(), get_max=True)
+        # per-slice costs (float64 accumulate of the reference's per-sample terms is not available; keep total)
+        out.update(syn_cost=c.detach(), syn_cost_max=cmax, syn_gx_sum=x5.grad[:, :2, :].double().sum(dim=(0,)).numpy(),
+                   syn_gx_abs=np.float64(x5.grad.abs().double().sum()), syn_grho_sum=r.grad.double().sum(dim=0).numpy()[0],
+                   syn_gx_head=x5.grad[:64, :2, :], syn_grho_head=r.grad[:64, 0, :])
+        save("env_seed%d.npz" % seed, **out)
+
+
+def gen_data(car, args):
+    """compute_data (data_generation/compute_rawdata.py:9) with a fixed seed: RNG-order golden (config 1)."""
+    rh.install()
+    with rh.ref_cwd():
+        from data_generation.compute_rawdata import compute_data
+        torch.manual_seed(5)
+        res = compute_data([1, 2], 20, car, args, samples_t=10, save=False, plot=False)
+    out = {}
+    for i, r in enumerate(res):
+        for k, v in r.items():
+            out["r%d_%s" % (i, k)] = v
+    save("compute_data.npz", **out)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="weights,rollout,step,grid,env,data")
+    ap.add_argument("--env-seeds", default="0,1,2,3,4,5,6,7,8,9")
+    a = ap.parse_args()
+    which = a.only.split(",")
+    car, args = rh.make_car()
+    t0 = time.time()
+    if "weights" in which:
+        export_weights(car)
+    if "rollout" in which:
+        gen_rollout(car, args)
+    if "step" in which:
+        gen_step(car, args)
+    if "grid" in which:
+        gen_grid(car, args)
+    if "data" in which:
+        gen_data(car, args)
+    if "env" in which:
+        gen_env(car, args, [int(s) for s in a.env_seeds.split(",")])
+    print("done in %.1f s" % (time.time() - t0))
+
+
+if __name__ == "__main__":
+    main()
