@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the density_planner hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework's arm
+    python bench.py --impl reference [--gpus N] ...                 # CPU arm: the oracle port on the host cores
+
+One "step" = one pass of the hot path over one batch of synthetic input on every rank:
+    fused rollout of SAMPLES x STEPS closed-loop sample-steps with Liouville log-density (BASELINE config 2:
+    1M samples x 100 steps), slices stored every 10th step  ->  density normaliser  ->  collision cost on the stored
+    slices  ->  occupancy binning of the slices (int64/int32 grids)  [-> NCCL allreduce of normaliser stats, cost and
+    grids when N > 1].
+`value` = closed-loop sample-steps/s over all ranks with inputs resident in HBM (CUDA events, max over ranks).
+`e2e`   = the same metric through the public API `Car.compute_density` with HOST tensors (H2D + kernel + D2H of the
+          full trajectory inside the timed region).
+Multi-GPU is weak scaling: every rank rolls out its own SAMPLES samples; no collective in the rollout.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SAMPLES = 1_000_000
+STEPS = 100
+STRIDE = 10
+FLOP_PER_SAMPLE_STEP = 248_288  # SURVEY section 8d / DESIGN.md: algorithmic FLOPs (124,144 MAC) per sample-step
+METRIC = "closed-loop sample-steps/sec with Liouville density"
+UNIT = "sample-steps/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_env(args, seed, device):
+    """Synthetic occupancy environment of the reference's shape (241 x 401 x 101, time innermost): street walls plus
+    random static / moving boxes with graded certainty, and centred-difference gradients (border value 1)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    G0, G1, Tg = args.grid_size[0], args.grid_size[1], 101
+    grid = torch.zeros(G0, G1, Tg)
+    grid[:35, :, :] = 1.0
+    grid[-35:, :, :] = 1.0
+    for _ in range(12):
+        w, h = [int(v) for v in torch.randint(5, 40, (2,), generator=g)]
+        x0 = int(torch.randint(45, G0 - 45 - w, (1,), generator=g))
+        y0 = int(torch.randint(60, G1 - 60 - h, (1,), generator=g))
+        cert = float(torch.randint(3, 10, (1,), generator=g)) / 10
+        vx, vy = [int(v) for v in torch.randint(-2, 2, (2,), generator=g)]
+        moving = bool(torch.rand(1, generator=g) < 0.6)
+        for t in range(Tg):
+            xs = x0 + (vx * t if moving else 0)
+            ys = y0 + (vy * t if moving else 0)
+            for ring in range(4):
+                a0, a1 = max(xs - ring, 0), min(xs + w + ring, G0)
+                b0, b1 = max(ys - ring, 0), min(ys + h + ring, G1)
+                if a1 > a0 and b1 > b0:
+                    grid[a0:a1, b0:b1, t] += cert / 4
+    grid = grid.clamp(0, 1).to(device)
+    pad = torch.nn.functional.pad
+    gx = (pad(grid, (0, 0, 0, 0, 1, 0), value=1.0)[:-1] - pad(grid, (0, 0, 0, 0, 0, 1), value=1.0)[1:]) / 2
+    gy = (pad(grid, (0, 0, 1, 0), value=1.0)[:, :-1] - pad(grid, (0, 0, 0, 1), value=1.0)[:, 1:]) / 2
+    return grid, gx, gy
+
+
+def cpu_oracle_rate(target_seconds=12.0):
+    """Times the CPU restatement (oracle/dp_oracle.c, OpenMP over samples) on a bounded sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import dp_oracle as O
+    import torch
+    import density_planner_b200 as dp
+    blob = O.load_weights()
+    a = dp.default_args()
+    car = dp.Car(a)
+    torch.manual_seed(0)
+    up, uref, xref = car.get_valid_ref(a)
+    uref, xref = uref[0, :, :STEPS].numpy(), xref[0, :, :STEPS + 1].numpy()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    n_probe = max(cores * 8, 64)
+    xe0 = car.sample_xe0(n_probe)[:, :, 0].numpy()
+    t0 = time.perf_counter()
+    O.rollout(blob, xe0, xref, uref, a.dt_sim, stride=STRIDE)
+    rate = n_probe * STEPS / (time.perf_counter() - t0)
+    n = int(min(max(rate * target_seconds / STEPS, n_probe), SAMPLES))
+    xe0 = car.sample_xe0(n)[:, :, 0].numpy()
+    t0 = time.perf_counter()
+    O.rollout(blob, xe0, xref, uref, a.dt_sim, stride=STRIDE)
+    dt = time.perf_counter() - t0
+    return {"value": n * STEPS / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d samples x %d steps of the same rollout (C restatement of the reference's compute_density, "
+                      "analytic divergence, OpenMP over samples), %.1f s" % (n, STEPS, dt)}, n, dt
+
+
+def run_reference_arm(opts):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    base = None
+    times = []
+    for i in range(opts.warmup + opts.steps):
+        base, n, dt = cpu_oracle_rate(target_seconds=6.0 if opts.steps > 1 else 12.0)
+        if i >= opts.warmup:
+            times.append((n, dt))
+        if time.perf_counter() - t_all > 240:
+            break
+    tot_n = sum(n for n, _ in times)
+    tot_t = sum(dt for _, dt in times)
+    value = tot_n * STEPS / tot_t
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": opts.gpus,
+            "steps": len(times), "warmup": opts.warmup, "ms_per_step": 1e3 * tot_t / max(len(times), 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "CAR rollout + Liouville density, %d samples x %d steps per GPU (config 2); CPU arm "
+                                   "runs a bounded sample of it on the host cores" % (SAMPLES, STEPS)},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--kernel", default=None, choices=[None, "ffma", "tc"], help="rollout kernel (default: library default)")
+    ap.add_argument("--samples", type=int, default=SAMPLES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    opts = ap.parse_args()
+    if opts.impl == "reference":
+        return run_reference_arm(opts)
+
+    import torch
+    import density_planner_b200 as dp
+    from density_planner_b200 import _lib, dist as D, grid as G
+    import ctypes
+
+    rank, world, local_rank = D.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    L = dp.lib()
+    args = dp.default_args()
+    car = dp.Car(args, device=dev)
+    N, T, Ts = opts.samples, STEPS, STEPS // STRIDE + 1
+
+    # ---- synthetic inputs (seeded; rank r uses seed r for its samples) --------------------------------------------
+    torch.manual_seed(0)
+    up, uref, xref = car.get_valid_ref(args)
+    uref, xref = uref[:, :, :T].contiguous(), xref[:, :, :T + 1].contiguous()
+    torch.manual_seed(1000 + rank)
+    xe0_host = car.sample_xe0(N).pin_memory()
+    rho0_host = (torch.rand(N) + 0.5)
+    rho0_host = (rho0_host / (rho0_host.sum() * world)).pin_memory()
+    xe0 = xe0_host.reshape(N, 5).to(dev)
+    rho0 = rho0_host.to(dev)
+    xref_d, uref_d = xref.reshape(5, T + 1).to(dev), uref.reshape(2, T).to(dev)
+    grid, gx, gy = synthetic_env(args, 0, dev)
+    denv = dp.DeviceEnv(grid, gx, gy, args, device=dev)
+    del grid, gx, gy
+
+    impl_flag = {None: _lib.DP_IMPL_DEFAULT, "ffma": _lib.DP_IMPL_FFMA, "tc": _lib.DP_IMPL_TC}[opts.kernel]
+    flags = _lib.DP_LOG_DENSITY | _lib.DP_DENSITY | impl_flag
+    x_out = torch.empty((Ts, 5, N), dtype=torch.float32, device=dev)
+    l_out = torch.empty((Ts, N), dtype=torch.float32, device=dev)
+    rho = torch.empty((Ts, N), dtype=torch.float32, device=dev)
+    lmax = torch.empty(Ts, dtype=torch.float32, device=dev)
+    lsum = torch.empty(Ts, dtype=torch.float64, device=dev)
+    cost_slices = torch.empty(Ts, dtype=torch.float64, device=dev)
+    spec = _lib.BinSpec()
+    spec.mode = 0
+    spec.geom = G._geom(args)
+    spec.mass_scale_log2 = G.mass_scale_log2(N * world, 1.0)
+    cells = (args.grid_size[0] + 1) * (args.grid_size[1] + 1)
+    mass = torch.zeros((Ts, cells), dtype=torch.int64, device=dev)
+    count = torch.zeros((Ts, cells), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(opts.steps)]
+    ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(opts.steps)]
+    launches = {"n": 0}
+
+    def one_step(i_timed=None):
+        if i_timed is not None:
+            ev_k0[i_timed].record(stream)
+        _lib.check(L.dp_rollout(car.controller.controller.handle, _lib.ptr(xe0), _lib.ptr(xref_d), _lib.ptr(uref_d), None,
+                                float(args.dt_sim), N, T, flags, STRIDE, _lib.ptr(x_out), _lib.ptr(l_out), N, None, None,
+                                sp), "dp_rollout")
+        if i_timed is not None:
+            ev_k1[i_timed].record(stream)
+        _lib.check(L.dp_normalize_stats(_lib.ptr(l_out), _lib.ptr(rho0), N, Ts, N, _lib.ptr(lmax), _lib.ptr(lsum), sp),
+                   "dp_normalize_stats")
+        gmax, gsum = D.merge_normalizer_stats(lmax, lsum)
+        _lib.check(L.dp_normalize_apply(_lib.ptr(l_out), _lib.ptr(rho0), N, Ts, N, _lib.ptr(gmax), _lib.ptr(gsum),
+                                        _lib.ptr(rho), sp), "dp_normalize_apply")
+        xs, ys = x_out[:, 0, :], x_out[:, 1, :]
+        _lib.check(L.dp_cost_coll(denv.handle, _lib.ptr(xs), _lib.ptr(ys), 1, 5 * N, _lib.ptr(rho), 1, N, N, Ts, 0,
+                                  _lib.ptr(cost_slices), None, None, None, None, 0, 0, None, sp), "dp_cost_coll")
+        mass.zero_()
+        count.zero_()
+        _lib.check(L.dp_bin2d(ctypes.byref(spec), _lib.ptr(xs), _lib.ptr(ys), 1, 5 * N, _lib.ptr(rho), 1, N, N, Ts,
+                              _lib.ptr(mass), _lib.ptr(count), sp), "dp_bin2d")
+        D.allreduce_sum(cost_slices)
+        D.allreduce_grids(mass, count)
+        # rollout, normalize_stats, normalize_apply, cost (+finalize), 2 memsets, bin2d  (+ NCCL kernels when N > 1)
+        launches["n"] += 8
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(opts.warmup, 3)):
+        one_step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches["n"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(opts.steps):
+        one_step(i)
+    e1.record(stream)
+    barrier()
+    ms_total = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / opts.steps
+    value = world * N * T / (ms_step * 1e-3)
+    k_ms = sum(a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)) / opts.steps
+    k_ms = D.max_over_ranks(k_ms, dev)
+    total_mass = int(mass.sum().item())
+    total_count = int(count.sum().item())
+    cost_total = float(cost_slices.sum().item())
+
+    # ---- end to end through the public API with host tensors ---------------------------------------------------------
+    xe0_cpu = xe0_host  # (N,5,1) pinned
+    impl = opts.kernel
+    car.compute_density(xe0_cpu[:1024], xref, uref, args.dt_sim, log_density=True, impl=impl)  # warm the host path
+    barrier()
+    e2e_steps = max(1, min(opts.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        xe_traj, rho_traj = car.compute_density(xe0_cpu, xref, uref, args.dt_sim, log_density=True, cutting=True, impl=impl)
+        _ = float(rho_traj[0, 0, -1])
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    t_e2e = D.max_over_ranks(t_e2e, dev)
+    e2e = {"value": world * N * T / t_e2e, "unit": UNIT,
+           "h2d_bytes_per_step": int(4 * (N * 5 + 5 * (T + 1) + 2 * T)),
+           "d2h_bytes_per_step": int(4 * (T + 1) * 6 * N),
+           "api": "Car.compute_density(xe0, xref_traj, uref_traj, dt, log_density=True) with CPU tensors "
+                  "(dp_rollout_host: H2D + kernel + D2H of the full (N,5,T+1)+(N,1,T+1) trajectory)",
+           "ms_per_step": 1e3 * t_e2e}
+    del xe_traj, rho_traj
+
+    # ---- collision cost / binning throughput on the stored slices (second half of the metric) ---------------------
+    xs, ys = x_out[:, 0, :], x_out[:, 1, :]
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    for r in range(reps + 3):
+        if r == 3:
+            c0.record(stream)
+        _lib.check(L.dp_cost_coll(denv.handle, _lib.ptr(xs), _lib.ptr(ys), 1, 5 * N, _lib.ptr(rho), 1, N, N, Ts, 0,
+                                  _lib.ptr(cost_slices), None, None, None, None, 0, 0, None, sp), "dp_cost_coll")
+    c1.record(stream)
+    torch.cuda.synchronize(dev)
+    cost_ms = c0.elapsed_time(c1) / reps
+    cost_evals = N * Ts / (cost_ms * 1e-3)
+
+    if rank != 0:
+        return
+    peaks, peaks_src = measured_peaks()
+    tf_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    achieved_tf = N * T * FLOP_PER_SAMPLE_STEP / (k_ms * 1e-3) / 1e12
+    ffma_tf = ctypes.c_double(0)
+    L.dp_probe_ffma_peak(local_rank, ctypes.byref(ffma_tf))
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("rollout_dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / tf_peak, "traffic": traffic,
+                "kernel": "rollout (%s)" % (opts.kernel or "default"), "kernel_ms": k_ms,
+                "peak_source": "%s bf16_tflops_sustained (dense tensor pipe; the rollout is a K=128 dense contraction)" % peaks_src,
+                "algorithmic_flop_per_sample_step": FLOP_PER_SAMPLE_STEP,
+                "fp32_ffma_peak_tflops_measured": ffma_tf.value,
+                "frac_of_fp32_ffma_peak": achieved_tf / ffma_tf.value if ffma_tf.value else None,
+                "hbm_bytes_per_launch_algorithmic": int(4 * Ts * 6 * N + 4 * 5 * N),
+                "cost_kernel": {"bound": "hbm", "evals_per_s": cost_evals, "achieved": 12 * cost_evals / 1e9,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": 12 * cost_evals / 1e9 / peaks["hbm_gbs"],
+                                "bytes_per_eval": 12}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": opts.steps, "warmup": max(opts.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "CAR rollout + Liouville density, %d samples x %d steps per GPU (BASELINE config 2), "
+                                   "then normaliser + collision cost + occupancy binning on %d stored slices" % (N, T, Ts),
+                       "samples_per_gpu": N, "horizon_steps": T, "stored_slices": Ts,
+                       "controller": "trained C3M controller_CAR_3layers (43,592 fp32 weights)",
+                       "l2_policy": "inputs+outputs per step (%.0f MB written) exceed the 126 MB L2" % (4e-6 * Ts * 6 * N),
+                       "parallelism": "samples sharded, %d rank(s); allreduce of normaliser stats, cost and int grids" % world},
+            "e2e": e2e, "gpu_launches": launches["n"], "clocks": clk, "roofline": roofline,
+            "collision_cost_evals_per_s": cost_evals * world,
+            "checks": {"grid_count_total": total_count, "grid_mass_total": total_mass, "cost_total": cost_total}}
+    if not opts.no_cpu_baseline and world == 1:
+        base, _, _ = cpu_oracle_rate()
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

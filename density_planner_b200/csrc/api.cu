@@ -1,0 +1,211 @@
+// C ABI glue: error state, controller objects, rollout dispatch, host-buffer entry points, FFMA peak probe.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "dp_common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void dp_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+int dp_abi_version(void) { return DP_ABI_VERSION; }
+const char *dp_last_error(void) { return g_err; }
+
+int dp_device_ok(int device) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        dp_set_error("cudaGetDeviceProperties(%d) failed", device);
+        return -1;
+    }
+    return prop.major == 10 ? 1 : 0;
+}
+
+int dp_controller_create(const float *blob, size_t n_floats, int device, dp_controller **out) {
+    DP_REQUIRE(blob && out, "dp_controller_create: null argument");
+    DP_REQUIRE(n_floats == DP_CONTROLLER_BLOB_FLOATS, "dp_controller_create: blob has %zu floats, expected %d", n_floats,
+               DP_CONTROLLER_BLOB_FLOATS);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    DP_CUDA(cudaGetDeviceProperties(&prop, device));
+    DP_REQUIRE(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a (B200) only and has no fallback",
+               device, prop.major, prop.minor);
+    std::vector<float> big(DP_BIG_FLOATS), small(DP_SMALL_FLOATS);
+    const float *p = blob;
+    const int nouts[2] = {DP_NOUT_A, DP_NOUT_B};
+    const int big_w2[2] = {DP_BIG_W2A, DP_BIG_W2B}, big_w3[2] = {DP_BIG_W3A, DP_BIG_W3B};
+    const int small_net[2] = {DP_SM_NET_A, DP_SM_NET_B};
+    for (int m = 0; m < 2; ++m) {
+        const int no = nouts[m];
+        float *sm = small.data() + small_net[m];
+        memcpy(sm + DP_SM_W1, p, sizeof(float) * DP_HID * 4); p += DP_HID * 4;
+        memcpy(sm + DP_SM_B1, p, sizeof(float) * DP_HID); p += DP_HID;
+        const float *W2 = p; p += DP_HID * DP_HID;
+        memcpy(sm + DP_SM_B2, p, sizeof(float) * DP_HID); p += DP_HID;
+        const float *W3 = p; p += no * DP_HID;
+        memcpy(sm + DP_SM_B3, p, sizeof(float) * no); p += no;
+        for (int j = 0; j < DP_HID; ++j)
+            for (int k = 0; k < DP_HID; ++k) big[big_w2[m] + k * DP_HID + j] = W2[j * DP_HID + k];
+        for (int j = 0; j < no; ++j)
+            for (int k = 0; k < DP_HID; ++k) big[big_w3[m] + k * no + j] = W3[j * DP_HID + k];
+    }
+    dp_controller *c = new dp_controller();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    DP_CUDA(cudaMalloc(&c->d_big, sizeof(float) * DP_BIG_FLOATS));
+    DP_CUDA(cudaMalloc(&c->d_small, sizeof(float) * DP_SMALL_FLOATS));
+    DP_CUDA(cudaMemcpy(c->d_big, big.data(), sizeof(float) * DP_BIG_FLOATS, cudaMemcpyHostToDevice));
+    DP_CUDA(cudaMemcpy(c->d_small, small.data(), sizeof(float) * DP_SMALL_FLOATS, cudaMemcpyHostToDevice));
+    DP_CUDA(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
+    if (dp_tc_prepare(c, blob) != 0) {
+        dp_controller_destroy(c);
+        return 3;
+    }
+    *out = c;
+    return 0;
+}
+
+void dp_controller_destroy(dp_controller *c) {
+    if (!c) return;
+    DeviceGuard guard(c->device);
+    dp_tc_release(c);
+    cudaFree(c->d_big);
+    cudaFree(c->d_small);
+    cudaFree(c->ws.ptr);
+    if (c->host_stream) cudaStreamDestroy(c->host_stream);
+    delete c;
+}
+
+int dp_rollout(const dp_controller *c, const float *xe0, const float *xref, const float *uref, const float *rho0, float dt,
+               int64_t N, int T, unsigned flags, int stride, float *x_out, float *rho_out, int64_t ldn, float *clip_margin,
+               int *status, void *stream) {
+    DP_REQUIRE(c && xe0 && xref && uref, "dp_rollout: null argument");
+    DP_REQUIRE(T >= 0 && stride >= 1, "dp_rollout: bad T=%d / stride=%d", T, stride);
+    DP_REQUIRE(ldn >= N || (!x_out && !rho_out), "dp_rollout: ldn=%lld < N=%lld", (long long)ldn, (long long)N);
+    if (N <= 0) return 0;
+    DeviceGuard guard(c->device);
+    RolloutParams p;
+    p.big = c->d_big; p.small = c->d_small; p.tc = c->d_tc;
+    p.xe0 = xe0; p.xref = xref; p.uref = uref; p.rho0 = rho0;
+    p.dt = dt; p.N = N; p.T = T; p.flags = flags; p.stride = stride; p.Ts = T / stride + 1;
+    p.x_out = x_out; p.rho_out = rho_out; p.ldn = ldn; p.clip_margin = clip_margin; p.status = status;
+    const unsigned impl = flags & DP_IMPL_MASK;
+    if (impl == DP_IMPL_TC) return dp_launch_rollout_tc(c, p, (cudaStream_t)stream);
+    if (impl == DP_IMPL_FFMA || impl == DP_IMPL_DEFAULT) return dp_launch_rollout_ffma(c, p, (cudaStream_t)stream);
+    dp_set_error("dp_rollout: unknown implementation selector 0x%x", impl);
+    return 2;
+}
+
+static int ws_reserve(dp_controller *c, size_t bytes) {
+    if (c->ws.bytes >= bytes) return 0;
+    if (c->ws.ptr) cudaFree(c->ws.ptr);
+    c->ws.ptr = nullptr;
+    c->ws.bytes = 0;
+    DP_CUDA(cudaMalloc(&c->ws.ptr, bytes));
+    c->ws.bytes = bytes;
+    return 0;
+}
+
+int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const float *uref, const float *rho0, float dt,
+                    int64_t N, int T, unsigned flags, int stride, float *x_out, float *rho_out, float *clip_margin,
+                    int *status) {
+    DP_REQUIRE(c && xe0 && xref && uref, "dp_rollout_host: null argument");
+    DP_REQUIRE(T >= 0 && stride >= 1, "dp_rollout_host: bad T / stride");
+    if (N <= 0) return 0;
+    DeviceGuard guard(c->device);
+    const int Ts = T / stride + 1;
+    const int nd = (flags & DP_XY_ONLY) ? 2 : 5;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_xe0 = al(sizeof(float) * N * 5), b_xref = al(sizeof(float) * 5 * (T + 1)), b_uref = al(sizeof(float) * 2 * (T > 0 ? T : 1));
+    const size_t b_rho0 = rho0 ? al(sizeof(float) * N) : 0;
+    const size_t b_x = x_out ? al(sizeof(float) * (size_t)Ts * nd * N) : 0;
+    const size_t b_rho = rho_out ? al(sizeof(float) * (size_t)Ts * N) : 0;
+    const size_t b_m = clip_margin ? al(sizeof(float) * N) : 0;
+    const size_t b_st = 256;
+    if (ws_reserve(c, b_xe0 + b_xref + b_uref + b_rho0 + b_x + b_rho + b_m + b_st)) return 1;
+    char *base = (char *)c->ws.ptr;
+    float *d_xe0 = (float *)base; base += b_xe0;
+    float *d_xref = (float *)base; base += b_xref;
+    float *d_uref = (float *)base; base += b_uref;
+    float *d_rho0 = rho0 ? (float *)base : nullptr; base += b_rho0;
+    float *d_x = x_out ? (float *)base : nullptr; base += b_x;
+    float *d_rho = rho_out ? (float *)base : nullptr; base += b_rho;
+    float *d_m = clip_margin ? (float *)base : nullptr; base += b_m;
+    int *d_st = (int *)base;
+    cudaStream_t st = c->host_stream;
+    DP_CUDA(cudaMemcpyAsync(d_xe0, xe0, sizeof(float) * N * 5, cudaMemcpyHostToDevice, st));
+    DP_CUDA(cudaMemcpyAsync(d_xref, xref, sizeof(float) * 5 * (T + 1), cudaMemcpyHostToDevice, st));
+    if (T > 0) DP_CUDA(cudaMemcpyAsync(d_uref, uref, sizeof(float) * 2 * T, cudaMemcpyHostToDevice, st));
+    if (rho0) DP_CUDA(cudaMemcpyAsync(d_rho0, rho0, sizeof(float) * N, cudaMemcpyHostToDevice, st));
+    DP_CUDA(cudaMemsetAsync(d_st, 0, 2 * sizeof(int), st));
+    int rc = dp_rollout(c, d_xe0, d_xref, d_uref, d_rho0, dt, N, T, flags, stride, d_x, d_rho, N, d_m, d_st, st);
+    if (rc) return rc;
+    if (x_out) DP_CUDA(cudaMemcpyAsync(x_out, d_x, sizeof(float) * (size_t)Ts * nd * N, cudaMemcpyDeviceToHost, st));
+    if (rho_out) DP_CUDA(cudaMemcpyAsync(rho_out, d_rho, sizeof(float) * (size_t)Ts * N, cudaMemcpyDeviceToHost, st));
+    if (clip_margin) DP_CUDA(cudaMemcpyAsync(clip_margin, d_m, sizeof(float) * N, cudaMemcpyDeviceToHost, st));
+    int h_st[2] = {0, 0};
+    DP_CUDA(cudaMemcpyAsync(h_st, d_st, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    DP_CUDA(cudaStreamSynchronize(st));
+    if (status) { status[0] = h_st[0]; status[1] = h_st[1]; }
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- FFMA peak probe ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float *out, int iters, float a, float b) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    if (s == 12345.678f) out[0] = s;
+}
+}  // namespace
+
+extern "C" int dp_probe_ffma_peak(int device, double *tflops) {
+    DP_REQUIRE(tflops, "dp_probe_ffma_peak: null argument");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    DP_CUDA(cudaGetDeviceProperties(&prop, device));
+    float *d;
+    DP_CUDA(cudaMalloc(&d, 4));
+    const int iters = 20000, blocks = prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1;
+    DP_CUDA(cudaEventCreate(&e0));
+    DP_CUDA(cudaEventCreate(&e1));
+    ffma_probe_kernel<<<blocks, 256>>>(d, 1000, 0.999f, 0.001f);
+    DP_CUDA(cudaDeviceSynchronize());
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        DP_CUDA(cudaEventRecord(e0));
+        ffma_probe_kernel<<<blocks, 256>>>(d, iters, 0.999f, 0.001f);
+        DP_CUDA(cudaEventRecord(e1));
+        DP_CUDA(cudaEventSynchronize(e1));
+        float ms;
+        DP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 128.0 * iters * 256.0 * blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return 0;
+}

@@ -1,0 +1,388 @@
+// K2: collision cost, forward + analytic backward, and the environment table it gathers from.
+//   MotionPlanner.get_cost_coll              motion_planning/MotionPlanner.py:192-224
+//   MotionPlannerGrad.get_cost_coll_initialize  motion_planning/MotionPlannerGrad.py:309-336
+//   pos2gridpos / gridpos2pos                motion_planning/utils.py:70-116
+// HBM-bound: 12 B streamed per (sample, slice) forward (+12 B gradients), one 16-byte gather from a time-major
+// {p, gradX, gradY} table that stays L2-resident because samples cluster around the reference trajectory.
+#include "dp_common.cuh"
+
+namespace {
+
+constexpr int CB = 256;  // threads per block
+constexpr int MAX_PARTIALS = 1 << 16;
+
+struct Geom {
+    float x_lo, x_rng, y_lo, y_rng, gxm1, gym1;
+    int gx, gy;
+};
+
+__host__ __device__ inline Geom make_geom(const dp_grid_geom &g) {
+    Geom q;
+    q.x_lo = g.x_min;
+    q.x_rng = g.x_max - g.x_min;
+    q.y_lo = g.y_min;
+    q.y_rng = g.y_max - g.y_min;
+    q.gxm1 = (float)(g.gx - 1);
+    q.gym1 = (float)(g.gy - 1);
+    q.gx = g.gx;
+    q.gy = g.gy;
+    return q;
+}
+
+// one (sample, slice) evaluation.  Returns the fp32 term rho*p*sq (0 if inactive) and optionally the gradients.
+struct Eval {
+    float term, gx, gy, grho;
+    bool active;
+};
+
+__device__ __forceinline__ Eval eval_one(const float4 *__restrict__ table, const Geom &q, int t, float x, float y, float rho,
+                                         bool has_rho) {
+    int ix = dp_cell(x, q.x_lo, q.x_rng, q.gxm1);
+    int iy = dp_cell(y, q.y_lo, q.y_rng, q.gym1);
+    ix = min(max(ix, 0), q.gx - 1);  // :208-209
+    iy = min(max(iy, 0), q.gy - 1);
+    const float4 e = __ldg(table + ((size_t)t * q.gx + ix) * q.gy + iy);  // {p, gradX, gradY, 0}
+    Eval r;
+    r.active = (e.y != 0.0f) || (e.z != 0.0f);  // :213-214
+    // des_gridpos = gridpos + 100 * grad ; gridpos2pos ; squared distance (:215-218), each op rounded like torch
+    const float dgx = __fadd_rn(__int2float_rn(ix), __fmul_rn(100.0f, e.y));
+    const float dgy = __fadd_rn(__int2float_rn(iy), __fmul_rn(100.0f, e.z));
+    const float dpx = __fadd_rn(__fmul_rn(__fdiv_rn(dgx, q.gxm1), q.x_rng), q.x_lo);
+    const float dpy = __fadd_rn(__fmul_rn(__fdiv_rn(dgy, q.gym1), q.y_rng), q.y_lo);
+    const float ex = __fsub_rn(dpx, x), ey = __fsub_rn(dpy, y);
+    const float sq = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+    const float w = has_rho ? __fmul_rn(rho, e.x) : e.x;
+    r.term = r.active ? __fmul_rn(w, sq) : 0.0f;
+    r.gx = r.active ? __fmul_rn(-2.0f, __fmul_rn(w, ex)) : 0.0f;
+    r.gy = r.active ? __fmul_rn(-2.0f, __fmul_rn(w, ey)) : 0.0f;
+    r.grho = r.active ? __fmul_rn(e.x, sq) : 0.0f;
+    return r;
+}
+
+__device__ __forceinline__ double block_reduce_sum(double v, double *sh) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double tot = 0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sh[w];
+    return tot;  // valid in thread 0
+}
+__device__ __forceinline__ float block_reduce_max(float v, float *sh) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    float tot = -INFINITY;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot = fmaxf(tot, sh[w]);
+    return tot;
+}
+
+struct CostArgs {
+    const float4 *table;
+    Geom q;
+    const float *x, *y, *rho;
+    long long sx_n, sx_t, sr_n, sr_t, sg_n, sg_t;
+    long long N;
+    int Ts, get_max;
+    float *gx, *gy, *grho;
+    double *partial;      // [Ts][B]   sum mode
+    float *partial_max;   // [Ts][B]   max mode (-inf = no active sample)
+    double *cost_samples; // [N] or null (generic kernel only)
+    int B;
+};
+
+// (A) main path: samples contiguous (sx_n == 1).  grid (B, Ts): block (b, t) strides over the samples of slice t.
+__global__ void __launch_bounds__(CB) cost_nfast_kernel(CostArgs a) {
+    __shared__ double shd[CB / 32];
+    __shared__ float shf[CB / 32];
+    const int t = blockIdx.y;
+    const bool has_rho = a.rho != nullptr;
+    const float *xp = a.x + (long long)t * a.sx_t;
+    const float *yp = a.y + (long long)t * a.sx_t;
+    const float *rp = has_rho ? a.rho + (long long)t * a.sr_t : nullptr;
+    const bool want_g = a.gx != nullptr;
+    double acc = 0.0;
+    float mx = -INFINITY;
+    const long long stride = (long long)gridDim.x * CB;
+    for (long long n0 = (long long)blockIdx.x * CB + threadIdx.x; n0 < a.N; n0 += 4 * stride) {
+        float xv[4], yv[4], rv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long n = n0 + j * stride;
+            const bool ok = n < a.N;
+            xv[j] = ok ? __ldg(xp + n * a.sx_n) : 0.0f;
+            yv[j] = ok ? __ldg(yp + n * a.sx_n) : 0.0f;
+            rv[j] = (ok && has_rho) ? __ldg(rp + n * a.sr_n) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long n = n0 + j * stride;
+            if (n < a.N) {
+                const Eval e = eval_one(a.table, a.q, t, xv[j], yv[j], rv[j], has_rho);
+                acc += (double)e.term;
+                if (e.active) mx = fmaxf(mx, e.term);
+                if (want_g) {
+                    const long long o = n * a.sg_n + (long long)t * a.sg_t;
+                    a.gx[o] = e.gx;
+                    a.gy[o] = e.gy;
+                    if (a.grho) a.grho[o] = e.grho;
+                }
+            }
+        }
+    }
+    if (a.get_max) {
+        const float m = block_reduce_max(mx, shf);
+        if (threadIdx.x == 0) a.partial_max[(size_t)t * a.B + blockIdx.x] = m;
+    } else {
+        const double s = block_reduce_sum(acc, shd);
+        if (threadIdx.x == 0) a.partial[(size_t)t * a.B + blockIdx.x] = s;
+    }
+}
+
+// (G) generic strides / per-sample sums: one thread per sample loops over the slices; per-slice block reduction.
+__global__ void __launch_bounds__(128) cost_generic_kernel(CostArgs a) {
+    __shared__ double shd[4];
+    __shared__ float shf[4];
+    const long long n = (long long)blockIdx.x * 128 + threadIdx.x;
+    const bool ok = n < a.N;
+    const bool has_rho = a.rho != nullptr;
+    double mine = 0.0;
+    for (int t = 0; t < a.Ts; ++t) {
+        Eval e;
+        e.term = 0; e.gx = 0; e.gy = 0; e.grho = 0; e.active = false;
+        if (ok) {
+            const float x = __ldg(a.x + n * a.sx_n + (long long)t * a.sx_t);
+            const float y = __ldg(a.y + n * a.sx_n + (long long)t * a.sx_t);
+            const float r = has_rho ? __ldg(a.rho + n * a.sr_n + (long long)t * a.sr_t) : 0.0f;
+            e = eval_one(a.table, a.q, t, x, y, r, has_rho);
+            mine += (double)e.term;
+            if (a.gx) {
+                const long long o = n * a.sg_n + (long long)t * a.sg_t;
+                a.gx[o] = e.gx;
+                a.gy[o] = e.gy;
+                if (a.grho) a.grho[o] = e.grho;
+            }
+        }
+        if (a.get_max) {
+            const float m = block_reduce_max(e.active ? e.term : -INFINITY, shf);
+            if (threadIdx.x == 0) a.partial_max[(size_t)t * a.B + blockIdx.x] = m;
+        } else {
+            const double s = block_reduce_sum((double)e.term, shd);
+            if (threadIdx.x == 0) a.partial[(size_t)t * a.B + blockIdx.x] = s;
+        }
+    }
+    if (ok && a.cost_samples) a.cost_samples[n] = mine;
+}
+
+// fixed-order reduction of the per-block partials: slice sums and the total
+__global__ void cost_finalize_kernel(const double *partial, const float *partial_max, int B, int Ts, int get_max,
+                                     double *cost_slices, double *total) {
+    __shared__ double sh[1024];
+    double tot = 0.0;
+    for (int t = threadIdx.x; t < Ts; t += blockDim.x) {
+        double s = 0.0;
+        if (get_max) {
+            float m = -INFINITY;
+            for (int b = 0; b < B; ++b) m = fmaxf(m, partial_max[(size_t)t * B + b]);
+            s = (m == -INFINITY) ? 0.0 : (double)m;  // slices without an active sample add nothing (:213)
+        } else {
+            for (int b = 0; b < B; ++b) s += partial[(size_t)t * B + b];
+        }
+        if (cost_slices) cost_slices[t] = s;
+        tot += s;  // thread-local over t = tid, tid+blockDim, ... (fixed order)
+    }
+    sh[threadIdx.x] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0 && total) {
+        double s = 0.0;
+        for (int i = 0; i < (int)blockDim.x; ++i) s += sh[i];
+        *total = s;
+    }
+}
+
+__global__ void env_pack_kernel(const float *__restrict__ grid, const float *__restrict__ gradx,
+                                const float *__restrict__ grady, int G0, int G1, int Tg, float4 *__restrict__ table) {
+    // input (G0,G1,Tg) time innermost; output [t][ix][iy].  Tile-transposed through shared memory.
+    __shared__ float4 tile[32][33];
+    const long long cell0 = (long long)blockIdx.x * 32;  // cell = ix*G1 + iy
+    const int t0 = blockIdx.y * 32;
+    const long long cells = (long long)G0 * G1;
+    {
+        const int tl = threadIdx.x, cl = threadIdx.y;  // read: t fastest
+        for (int c = cl; c < 32; c += blockDim.y) {
+            const long long cell = cell0 + c;
+            const int t = t0 + tl;
+            if (cell < cells && t < Tg) {
+                const size_t i = (size_t)cell * Tg + t;
+                tile[c][tl] = make_float4(grid[i], gradx[i], grady[i], 0.0f);
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int cl = threadIdx.x, tl = threadIdx.y;  // write: cell fastest
+        for (int tt = tl; tt < 32; tt += blockDim.y) {
+            const long long cell = cell0 + cl;
+            const int t = t0 + tt;
+            if (cell < cells && t < Tg) table[(size_t)t * cells + cell] = tile[cl][tt];
+        }
+    }
+}
+
+}  // namespace
+
+// workspace for the partial sums lives with the environment (one in-flight dp_cost_coll per dp_env)
+struct dp_env_ws {
+    double *partial;
+    float *partial_max;
+};
+static dp_env_ws *env_ws(const dp_env *e);
+
+struct dp_env_full : dp_env {
+    dp_env_ws ws;
+};
+static dp_env_ws *env_ws(const dp_env *e) { return &static_cast<dp_env_full *>(const_cast<dp_env *>(e))->ws; }
+
+int dp_env_create(const dp_grid_geom *g, int Tg, const float *grid, const float *gradx, const float *grady, int on_device,
+                  int device, dp_env **out) {
+    DP_REQUIRE(g && grid && gradx && grady && out && Tg > 0 && g->gx > 1 && g->gy > 1, "dp_env_create: bad argument");
+    DeviceGuard guard(device);
+    dp_env_full *e = new dp_env_full();
+    e->device = device;
+    e->geom = *g;
+    e->Tg = Tg;
+    const size_t cells = (size_t)g->gx * g->gy, n = cells * Tg;
+    const float *d_in[3] = {grid, gradx, grady};
+    float *tmp[3] = {nullptr, nullptr, nullptr};
+    if (!on_device) {
+        for (int i = 0; i < 3; ++i) {
+            DP_CUDA(cudaMalloc(&tmp[i], n * sizeof(float)));
+            DP_CUDA(cudaMemcpy(tmp[i], d_in[i], n * sizeof(float), cudaMemcpyHostToDevice));
+            d_in[i] = tmp[i];
+        }
+    }
+    DP_CUDA(cudaMalloc(&e->d_table, n * sizeof(float4)));
+    DP_CUDA(cudaMalloc(&e->ws.partial, MAX_PARTIALS * sizeof(double)));
+    DP_CUDA(cudaMalloc(&e->ws.partial_max, MAX_PARTIALS * sizeof(float)));
+    dim3 blk(32, 8), grd((unsigned)((cells + 31) / 32), (unsigned)((Tg + 31) / 32));
+    env_pack_kernel<<<grd, blk>>>(d_in[0], d_in[1], d_in[2], g->gx, g->gy, Tg, e->d_table);
+    DP_CUDA(cudaGetLastError());
+    DP_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < 3; ++i)
+        if (tmp[i]) cudaFree(tmp[i]);
+    *out = e;
+    return 0;
+}
+
+void dp_env_destroy(dp_env *e0) {
+    if (!e0) return;
+    dp_env_full *e = static_cast<dp_env_full *>(e0);
+    DeviceGuard guard(e->device);
+    cudaFree(e->d_table);
+    cudaFree(e->ws.partial);
+    cudaFree(e->ws.partial_max);
+    delete e;
+}
+
+int dp_cost_coll(const dp_env *e, const float *x, const float *y, int64_t sx_n, int64_t sx_t, const float *rho,
+                 int64_t sr_n, int64_t sr_t, int64_t N, int Ts, int get_max, double *cost_slices, double *cost_samples,
+                 float *gx, float *gy, float *grho, int64_t sg_n, int64_t sg_t, double *total, void *stream_) {
+    DP_REQUIRE(e && x && y, "dp_cost_coll: null argument");
+    DP_REQUIRE(Ts >= 0 && Ts <= e->Tg, "dp_cost_coll: Ts=%d exceeds the %d time slices of the environment", Ts, e->Tg);
+    DP_REQUIRE((gx == nullptr) == (gy == nullptr), "dp_cost_coll: gx and gy must be given together");
+    DP_REQUIRE(!(grho && !gx), "dp_cost_coll: grho needs gx/gy");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DeviceGuard guard(e->device);
+    if (N <= 0 || Ts == 0) {
+        if (cost_slices && Ts > 0) DP_CUDA(cudaMemsetAsync(cost_slices, 0, sizeof(double) * Ts, stream));
+        if (total) DP_CUDA(cudaMemsetAsync(total, 0, sizeof(double), stream));
+        return 0;
+    }
+    CostArgs a;
+    a.table = e->d_table;
+    a.q = make_geom(e->geom);
+    a.x = x; a.y = y; a.rho = rho;
+    a.sx_n = sx_n; a.sx_t = sx_t; a.sr_n = sr_n; a.sr_t = sr_t; a.sg_n = sg_n; a.sg_t = sg_t;
+    a.N = N; a.Ts = Ts; a.get_max = get_max;
+    a.gx = gx; a.gy = gy; a.grho = grho;
+    a.partial = env_ws(e)->partial;
+    a.partial_max = env_ws(e)->partial_max;
+    a.cost_samples = cost_samples;
+    const bool nfast = (sx_n == 1) && (!rho || sr_n == 1) && (!gx || sg_n == 1) && !cost_samples;
+    if (nfast) {
+        long long B = (N + CB * 4 - 1) / (CB * 4);
+        const long long target = (148LL * 8 + Ts - 1) / Ts;  // ~8 resident blocks per SM over all slices
+        if (B > target) B = target;
+        if (B * Ts > MAX_PARTIALS) B = MAX_PARTIALS / Ts;
+        if (B < 1) B = 1;
+        a.B = (int)B;
+        DP_REQUIRE((long long)a.B * Ts <= MAX_PARTIALS, "dp_cost_coll: too many slices");
+        cost_nfast_kernel<<<dim3((unsigned)B, (unsigned)Ts), CB, 0, stream>>>(a);
+    } else {
+        const long long B = (N + 127) / 128;
+        DP_REQUIRE(B * Ts <= MAX_PARTIALS,
+                   "dp_cost_coll: strided/per-sample path supports N*Ts/128 <= %d (got N=%lld, Ts=%d); use the "
+                   "sample-contiguous [t][n] layout for large sample sets", MAX_PARTIALS, (long long)N, Ts);
+        a.B = (int)B;
+        cost_generic_kernel<<<(unsigned)B, 128, 0, stream>>>(a);
+    }
+    DP_CUDA(cudaGetLastError());
+    if (cost_slices || total) {
+        cost_finalize_kernel<<<1, 128, 0, stream>>>(a.partial, a.partial_max, a.B, Ts, get_max, cost_slices, total);
+        DP_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// ---- pos2gridpos / gridpos2pos as standalone ops -------------------------------------------------------------------
+namespace {
+__global__ void pos2gridpos_kernel(Geom q, const float *px, const float *py, long long n, int *ix, int *iy, int chx, int chy) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (px) {
+            int v = dp_cell(px[i], q.x_lo, q.x_rng, q.gxm1);
+            if (chx >= 0) v = min(max(v, 0), chx);
+            ix[i] = v;
+        }
+        if (py) {
+            int v = dp_cell(py[i], q.y_lo, q.y_rng, q.gym1);
+            if (chy >= 0) v = min(max(v, 0), chy);
+            iy[i] = v;
+        }
+    }
+}
+__global__ void gridpos2pos_kernel(Geom q, const float *gx, const float *gy, long long n, float *px, float *py) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (gx) px[i] = __fadd_rn(__fmul_rn(__fdiv_rn(gx[i], q.gxm1), q.x_rng), q.x_lo);
+        if (gy) py[i] = __fadd_rn(__fmul_rn(__fdiv_rn(gy[i], q.gym1), q.y_rng), q.y_lo);
+    }
+}
+}  // namespace
+
+int dp_pos2gridpos(const dp_grid_geom *g, const float *px, const float *py, int64_t n, int32_t *ix, int32_t *iy,
+                   int clamp_hi_x, int clamp_hi_y, void *stream) {
+    DP_REQUIRE(g && (!px || ix) && (!py || iy), "dp_pos2gridpos: bad argument");
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    pos2gridpos_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(make_geom(*g), px, py, n, ix, iy, clamp_hi_x,
+                                                                         clamp_hi_y);
+    DP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int dp_gridpos2pos(const dp_grid_geom *g, const float *gx, const float *gy, int64_t n, float *px, float *py, void *stream) {
+    DP_REQUIRE(g && (!gx || px) && (!gy || py), "dp_gridpos2pos: bad argument");
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    gridpos2pos_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(make_geom(*g), gx, gy, n, px, py);
+    DP_CUDA(cudaGetLastError());
+    return 0;
+}

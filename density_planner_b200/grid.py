@@ -1,0 +1,339 @@
+"""Grid layer: world<->grid transforms, occupancy binning and the collision cost, backed by the CUDA library.
+
+Reference surface mirrored here:
+  motion_planning/utils.py     pos2gridpos:70 gridpos2pos:100 pred2grid:255 check_collision:231
+  systems/utils.py             get_density_map:105
+  motion_planning/MotionPlanner.py       get_cost_coll:192        (forward + analytic backward)
+  motion_planning/MotionPlannerGrad.py   get_cost_coll_initialize:309
+  motion_planning/simulation_objects.py  EgoVehicle.predict_density normaliser :295-299
+
+`args` is the reference's hyper-parameter namespace (hyperparams.py): only `environment_size` and `grid_size`
+(and `bin_number` for get_density_map) are read.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _geom(args):
+    es, gs = args.environment_size, args.grid_size
+    return _lib.GridGeom(float(es[0]), float(es[1]), float(es[2]), float(es[3]), int(gs[0]), int(gs[1]))
+
+
+def _cuda_device(t=None):
+    if not torch.cuda.is_available():
+        raise _lib.DensityPlannerError("density_planner_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    if t is not None and t.is_cuda:
+        return t.device
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def pos2gridpos(args, pos_x=None, pos_y=None):
+    """World -> grid coordinates (motion_planning/utils.py:70-97); int64 tensors on the input's device."""
+    L = _lib.lib()
+    outs = []
+    for p, which in ((pos_x, 0), (pos_y, 1)):
+        if p is None:
+            outs.append(None)
+            continue
+        if isinstance(p, (list, tuple, np.ndarray)):
+            p = torch.as_tensor(np.asarray(p, dtype=np.float32))
+        dev = _cuda_device(p)
+        pd = p.detach().to(device=dev, dtype=torch.float32).contiguous()
+        idx = torch.empty(pd.shape, dtype=torch.int32, device=dev)
+        g = _geom(args)
+        with torch.cuda.device(dev):
+            if which == 0:
+                rc = L.dp_pos2gridpos(ctypes.byref(g), _lib.ptr(pd), None, pd.numel(), _lib.ptr(idx), None, -1, -1,
+                                      _lib.current_stream(dev))
+            else:
+                rc = L.dp_pos2gridpos(ctypes.byref(g), None, _lib.ptr(pd), pd.numel(), None, _lib.ptr(idx), -1, -1,
+                                      _lib.current_stream(dev))
+        _lib.check(rc, "dp_pos2gridpos")
+        outs.append(idx.to(device=p.device, dtype=torch.int64))
+    return outs[0], outs[1]
+
+
+def gridpos2pos(args, pos_x=None, pos_y=None):
+    """Grid -> world coordinates (motion_planning/utils.py:100-116)."""
+    L = _lib.lib()
+    outs = []
+    for p, which in ((pos_x, 0), (pos_y, 1)):
+        if p is None:
+            outs.append(None)
+            continue
+        p = torch.as_tensor(p)
+        dev = _cuda_device(p)
+        pd = p.detach().to(device=dev, dtype=torch.float32).contiguous()
+        o = torch.empty_like(pd)
+        g = _geom(args)
+        with torch.cuda.device(dev):
+            if which == 0:
+                rc = L.dp_gridpos2pos(ctypes.byref(g), _lib.ptr(pd), None, pd.numel(), _lib.ptr(o), None,
+                                      _lib.current_stream(dev))
+            else:
+                rc = L.dp_gridpos2pos(ctypes.byref(g), None, _lib.ptr(pd), pd.numel(), None, _lib.ptr(o),
+                                      _lib.current_stream(dev))
+        _lib.check(rc, "dp_gridpos2pos")
+        outs.append(o.to(p.device))
+    return outs[0], outs[1]
+
+
+def mass_scale_log2(n_total, max_weight=1.0):
+    """Fixed-point scale for the int64 mass accumulator: n_total weights of at most max_weight cannot overflow."""
+    bits = 62 - math.ceil(math.log2(max(n_total, 2))) - max(0, math.ceil(math.log2(max(max_weight, 1e-30))))
+    return int(max(0, min(bits, 52)))
+
+
+def bin2d_raw(spec, x, y, w, N, Ts, sx, sw, device):
+    """Integer binning: returns (mass int64 [Ts][cx][cy], count int32 [Ts][cx][cy]) on `device`."""
+    L = _lib.lib()
+    if spec.mode == 0:
+        cx, cy = spec.geom.gx + 1, spec.geom.gy + 1
+    else:
+        cx, cy = spec.bx, spec.by
+    mass = torch.zeros((Ts, cx, cy), dtype=torch.int64, device=device)
+    count = torch.zeros((Ts, cx, cy), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(L.dp_bin2d(ctypes.byref(spec), _lib.ptr(x), _lib.ptr(y), sx[0], sx[1], _lib.ptr(w), sw[0], sw[1], N, Ts,
+                              _lib.ptr(mass), _lib.ptr(count), _lib.current_stream(device)), "dp_bin2d")
+    return mass, count
+
+
+def pred2grid(x, rho, args, return_gridpos=False):
+    """Mean density per occupied cell, normalised to 1 (motion_planning/utils.py:255-280).
+
+    x (N,>=2,1), rho (N,1,1) -> grid (G0,G1,1).  Cell indices and per-cell counts are exact integers; the density mass
+    is accumulated in int64 fixed point (order-independent)."""
+    dev = _cuda_device(x)
+    N = x.shape[0]
+    xs = x.detach()[:, 0, 0].to(device=dev, dtype=torch.float32).contiguous()
+    ys = x.detach()[:, 1, 0].to(device=dev, dtype=torch.float32).contiguous()
+    w = rho.detach()[:, 0, 0].to(device=dev, dtype=torch.float32).contiguous()
+    spec = _lib.BinSpec()
+    spec.mode = 0
+    spec.geom = _geom(args)
+    wmax = float(w.abs().max()) if N > 0 else 1.0
+    spec.mass_scale_log2 = mass_scale_log2(N, wmax)
+    mass, count = bin2d_raw(spec, xs, ys, w, N, 1, (1, 0), (1, 0), dev)
+    G0, G1 = int(args.grid_size[0]), int(args.grid_size[1])
+    if bool((count[0, G0, :] > 0).any()) or bool((count[0, :, G1] > 0).any()):
+        # the reference clamps to G (not G-1) and then fails on the slice assignment (:262,:277); report it the same way
+        raise RuntimeError("pred2grid: samples beyond the upper grid edge (the reference raises here as well)")
+    cnt = count[0].to(torch.float64)
+    mean = torch.where(count[0] > 0, mass[0].to(torch.float64) / (2.0 ** spec.mass_scale_log2) / cnt.clamp(min=1),
+                       torch.zeros_like(cnt))
+    grid = (mean / mean.sum()).to(torch.float32)[:G0, :G1].unsqueeze(-1).to(x.device)
+    if return_gridpos:
+        gx, gy = pos2gridpos(args, pos_x=x[:, 0, 0], pos_y=x[:, 1, 0])
+        gridpos = torch.stack((gx.clamp(0, G0), gy.clamp(0, G1)), dim=1)
+        return grid, gridpos
+    return grid
+
+
+def check_collision(grid_ego, grid_env, max_coll_sum, return_coll_pos=False):
+    """Occupancy dot product (motion_planning/utils.py:231-252); plain tensor arithmetic on the caller's device."""
+    coll_grid = grid_ego * grid_env
+    coll_sum = coll_grid.sum()
+    collision = bool(coll_sum > max_coll_sum)
+    coll_pos_prob = None
+    if collision and return_coll_pos:
+        pos = coll_grid.nonzero(as_tuple=True)
+        coll_pos_prob = torch.stack((pos[0], pos[1], coll_grid[pos[0], pos[1]]))
+    return collision, coll_sum, coll_pos_prob
+
+
+def get_density_map(x, rho, args, log_density=False, type="LE", bins=None, bin_width=None, system=None):
+    """Error-state density histogram (systems/utils.py:105-129) -> (float64 numpy (bx,by), range_bins).
+
+    Like the reference, mutates `rho` in place (rho -= max / rho /= max)."""
+    if x.shape[1] != 2:
+        raise NotImplementedError("only the 2-D map used by the reference's callers is on the hot path")
+    if bins is None:
+        bins = args.bin_number[:x.shape[1]]
+    if bin_width is None:
+        bin_width = (system.XE_MAX - system.XE_MIN)[0, :x.shape[1], 0] / bins
+    if type != "MC" and log_density:
+        rho -= rho.max()
+        w = torch.exp(rho)
+    else:
+        rho /= rho.max()
+        w = rho
+    range_bins = [[float(-bins[i] * bin_width[i] / 2), float(bins[i] * bin_width[i] / 2)] for i in range(len(bins))]
+    dev = _cuda_device(x)
+    N = x.shape[0]
+    xs = x.detach()[:, 0].to(device=dev, dtype=torch.float32).contiguous()
+    ys = x.detach()[:, 1].to(device=dev, dtype=torch.float32).contiguous()
+    wd = w.detach().reshape(N).to(device=dev, dtype=torch.float32).contiguous()
+    spec = _lib.BinSpec()
+    spec.mode = 1
+    spec.lo_x, spec.hi_x = range_bins[0]
+    spec.lo_y, spec.hi_y = range_bins[1]
+    spec.bx, spec.by = int(bins[0]), int(bins[1])
+    spec.mass_scale_log2 = mass_scale_log2(N, 1.0)
+    mass, count = bin2d_raw(spec, xs, ys, wd, N, 1, (1, 0), (1, 0), dev)
+    density = (mass[0].to(torch.float64) / (2.0 ** spec.mass_scale_log2)).cpu().numpy()
+    mask = density > 0
+    if type != "MC":
+        density[mask] /= count[0].cpu().numpy()[mask]
+    density[mask] = density[mask] / density[mask].sum()
+    return density, range_bins
+
+
+def normalize_density(rho_log_unnorm, rho0):
+    """rho = exp(l - max_s l) * rho0 / sum_s(...) per time index (simulation_objects.py:295-299).
+
+    rho_log_unnorm (N,1,T) (any strides; the kernel's [T][N] storage is used without a copy), rho0 (N,1,1)."""
+    L = _lib.lib()
+    dev = _cuda_device(rho_log_unnorm)
+    N, T = rho_log_unnorm.shape[0], rho_log_unnorm.shape[2]
+    lt = rho_log_unnorm.detach()[:, 0, :].to(device=dev, dtype=torch.float32).t()  # (T, N)
+    if not lt.is_contiguous():
+        lt = lt.contiguous()
+    r0 = rho0.detach().reshape(N).to(device=dev, dtype=torch.float32).contiguous()
+    lmax = torch.empty(T, dtype=torch.float32, device=dev)
+    lsum = torch.empty(T, dtype=torch.float64, device=dev)
+    out = torch.empty((T, N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        s = _lib.current_stream(dev)
+        _lib.check(L.dp_normalize_stats(_lib.ptr(lt), _lib.ptr(r0), N, T, N, _lib.ptr(lmax), _lib.ptr(lsum), s),
+                   "dp_normalize_stats")
+        _lib.check(L.dp_normalize_apply(_lib.ptr(lt), _lib.ptr(r0), N, T, N, _lib.ptr(lmax), _lib.ptr(lsum),
+                                        _lib.ptr(out), s), "dp_normalize_apply")
+    return out.t().unsqueeze(1).to(rho_log_unnorm.device)
+
+
+class DeviceEnv:
+    """Device copy of an environment's occupancy grid and its gradients (simulation_objects.py:29-44,77-94), repacked
+    into the time-major gather table of the cost kernel.  Build once per environment."""
+
+    def __init__(self, grid, grid_gradientX, grid_gradientY, args, device=None):
+        L = _lib.lib()
+        dev = torch.device(device) if device is not None else _cuda_device(grid)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.args = args
+        G0, G1, Tg = grid.shape
+        if (G0, G1) != (int(args.grid_size[0]), int(args.grid_size[1])):
+            raise _lib.DensityPlannerError("grid shape %s does not match args.grid_size %s" % ((G0, G1), args.grid_size))
+        gs = [t.detach().to(device=dev, dtype=torch.float32).contiguous() for t in (grid, grid_gradientX, grid_gradientY)]
+        g = _geom(args)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            torch.cuda.current_stream(dev).synchronize()
+            _lib.check(L.dp_env_create(ctypes.byref(g), Tg, _lib.ptr(gs[0]), _lib.ptr(gs[1]), _lib.ptr(gs[2]), 1, dev.index,
+                                       ctypes.byref(h)), "dp_env_create")
+        self.handle = h
+        self.Tg = Tg
+
+    @classmethod
+    def from_env(cls, env, args, device=None):
+        """From a reference `Environment` object after get_gradient()."""
+        return cls(env.grid, env.grid_gradientX, env.grid_gradientY, args, device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().dp_env_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _cost_call(denv, x, y, rho, get_max, want_grad, per_sample):
+    """x, y: 2-D (N, Ts) fp32 device views (any strides); rho likewise or None."""
+    L = _lib.lib()
+    dev = denv.device
+    N, Ts = x.shape
+    total = torch.zeros(1, dtype=torch.float64, device=dev)
+    samples = torch.zeros(N, dtype=torch.float64, device=dev) if per_sample else None
+    gx = gy = gr = None
+    sg = (0, 0)
+    if want_grad:
+        # gradients in the layout of x (sample-contiguous if x is, else time-contiguous)
+        if x.stride(0) == 1:
+            gx = torch.empty((Ts, N), dtype=torch.float32, device=dev).t()
+            gy = torch.empty((Ts, N), dtype=torch.float32, device=dev).t()
+            gr = torch.empty((Ts, N), dtype=torch.float32, device=dev).t() if rho is not None else None
+        else:
+            gx = torch.empty((N, Ts), dtype=torch.float32, device=dev)
+            gy = torch.empty((N, Ts), dtype=torch.float32, device=dev)
+            gr = torch.empty((N, Ts), dtype=torch.float32, device=dev) if rho is not None else None
+        sg = (gx.stride(0), gx.stride(1))
+    assert x.stride() == y.stride()
+    with torch.cuda.device(dev):
+        _lib.check(L.dp_cost_coll(denv.handle, _lib.ptr(x), _lib.ptr(y), x.stride(0), x.stride(1), _lib.ptr(rho),
+                                  rho.stride(0) if rho is not None else 0, rho.stride(1) if rho is not None else 0,
+                                  N, Ts, 1 if get_max else 0, None, _lib.ptr(samples), _lib.ptr(gx), _lib.ptr(gy),
+                                  _lib.ptr(gr), sg[0], sg[1], _lib.ptr(total), _lib.current_stream(dev)), "dp_cost_coll")
+    return total, samples, gx, gy, gr
+
+
+def _as_dev_2d(t, dev):
+    """(N, Ts) fp32 view on `dev`, keeping strides when no copy is needed and one of them is 1."""
+    t = t.detach()
+    if t.device != dev or t.dtype != torch.float32:
+        t = t.to(device=dev, dtype=torch.float32)
+    if t.stride(0) != 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+class _CollisionCost(torch.autograd.Function):
+    """cost = sum_i sum_s rho[s,0,i] * p(cell) * |des(cell) - x[s,:2,i]|^2 with grid indices constant (no_grad, :206)."""
+
+    @staticmethod
+    def forward(ctx, x_traj, rho_traj, denv, get_max):
+        dev = denv.device
+        Ts = x_traj.shape[2]
+        x = _as_dev_2d(x_traj[:, 0, :], dev)
+        y = _as_dev_2d(x_traj[:, 1, :], dev)
+        if x.stride() != y.stride():
+            x, y = x.contiguous(), y.contiguous()
+        rho = _as_dev_2d(rho_traj[:, 0, :Ts], dev)
+        need = (x_traj.requires_grad or rho_traj.requires_grad) and not get_max
+        total, _, gx, gy, gr = _cost_call(denv, x, y, rho, get_max, need, False)
+        if need:
+            ctx.save_for_backward(gx, gy, gr)
+        ctx.meta = (x_traj.shape, rho_traj.shape, x_traj.device, rho_traj.device, Ts, need)
+        return total.to(dtype=torch.float32, device=x_traj.device)
+
+    @staticmethod
+    def backward(ctx, g):
+        xs, rs, xdev, rdev, Ts, need = ctx.meta
+        if not need:
+            raise RuntimeError("backward through get_cost_coll(get_max=True) is not supported by the kernel path")
+        gx, gy, gr = ctx.saved_tensors
+        gxt = grt = None
+        if ctx.needs_input_grad[0]:
+            gxt = torch.zeros(xs, dtype=torch.float32, device=xdev)
+            gxt[:, 0, :] = (gx * g.to(gx.device)).to(xdev)
+            gxt[:, 1, :] = (gy * g.to(gy.device)).to(xdev)
+        if ctx.needs_input_grad[1]:
+            grt = torch.zeros(rs, dtype=torch.float32, device=rdev)
+            grt[:, 0, :Ts] = (gr * g.to(gr.device)).to(rdev)
+        return gxt, grt, None, None
+
+
+def get_cost_coll(x_traj, rho_traj, denv, get_max=False):
+    """MotionPlanner.get_cost_coll (motion_planning/MotionPlanner.py:192-224): returns a (1,) fp32 tensor on
+    x_traj's device, differentiable w.r.t. x_traj[:, :2, :] and rho_traj (get_max=False)."""
+    return _CollisionCost.apply(x_traj, rho_traj, denv, bool(get_max))
+
+
+def get_cost_coll_initialize(x_traj, denv):
+    """MotionPlannerGrad.get_cost_coll_initialize (motion_planning/MotionPlannerGrad.py:309-336): per-trajectory cost
+    (num_traj,), no density weights.  Forward only here (the reference differentiates it w.r.t. the up parameters
+    through up2ref_traj; that autograd graph is SURVEY section 8f item 1, not yet kernel-backed)."""
+    dev = denv.device
+    x = _as_dev_2d(x_traj[:, 0, :], dev)
+    y = _as_dev_2d(x_traj[:, 1, :], dev)
+    if x.stride() != y.stride():
+        x, y = x.contiguous(), y.contiguous()
+    _, samples, _, _, _ = _cost_call(denv, x, y, None, False, False, True)
+    return samples.to(dtype=torch.float32, device=x_traj.device)

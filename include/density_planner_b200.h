@@ -1,0 +1,179 @@
+/*
+ * density_planner_b200.h -- C ABI of the B200-native hot path of MIT-REALM/density_planner.
+ *
+ * The reference is pure Python and has NO plugin / FFI interface for this path: the
+ * boundary it exposes is the Python method surface of systems/ControlAffineSystem.py, systems/sytem_CAR.py,
+ * motion_planning/utils.py and motion_planning/MotionPlanner.py.  Each entry point below names the reference
+ * method(s) (file:line under the reference root) whose arithmetic it replaces; INTEGRATION.md shows the ctypes
+ * binding a maintainer would add on the reference side.  density_planner_b200/ (Python) mirrors the reference
+ * method names on top of this ABI.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types.  Every function returns 0 on success, non-zero on error;
+ *     dp_last_error() returns a thread-local message for the last failure.
+ *   - "dev" pointers are device memory owned by the caller (e.g. torch allocations); "host" pointers are host
+ *     memory (pinned memory makes the *_host calls faster, pageable works).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device-pointer calls are asynchronous
+ *     on that stream; *_host calls copy in, run, copy out and synchronise before returning.
+ *   - all floating point data is fp32 unless noted.  Trajectories are stored time-major SoA:
+ *         x[t][d][n]  (t = stored time slot, d = state dim 0..4, n = sample)   rho[t][n]
+ *     which is the transposed view of the reference's (N, 5, T+1) / (N, 1, T+1) tensors.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef DENSITY_PLANNER_B200_H
+#define DENSITY_PLANNER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DP_ABI_VERSION 1
+
+/* ---- flags for dp_rollout* ------------------------------------------------------------------------------- */
+#define DP_LOG_DENSITY 1u  /* log_density=True: l += log(1 - div f * dt)  (ControlAffineSystem.py:147-157)      */
+#define DP_DENSITY 2u      /* compute_density=True (:409); off => rho_out untouched                             */
+#define DP_CUT 4u          /* cutting=True: clamp >1e30 (and <0 if linear), NaN -> 1e30 (:451-462)              */
+#define DP_ABS_STATE 8u    /* store x instead of the error state x - xref (the reference returns x - xref)      */
+#define DP_XY_ONLY 16u     /* store only state dims 0,1 (x_out is [Ts][2][ldn]) -- input of the collision cost  */
+/* kernel selection (bits 8..11); 0 = library default */
+#define DP_IMPL_MASK 0xF00u
+#define DP_IMPL_DEFAULT 0x000u
+#define DP_IMPL_FFMA 0x100u   /* fp32 CUDA-core kernel                                                         */
+#define DP_IMPL_TC 0x200u     /* tcgen05 tensor-core kernel, split-precision operands (fp32-level accuracy)    */
+
+/* number of fp32 values in a packed controller blob (see dp_controller_create) */
+#define DP_CONTROLLER_BLOB_FLOATS 43592
+
+typedef struct dp_controller dp_controller; /* immutable once created; shareable between threads */
+typedef struct dp_env dp_env;               /* occupancy grid + gradients of one environment, repacked on device */
+
+int dp_abi_version(void);
+const char *dp_last_error(void);
+/* 1 if the CUDA device `device` is an sm_100 part, 0 if not, <0 on error */
+int dp_device_ok(int device);
+
+/*
+ * The C3M controller (data/trained_controller/model_CAR.py:19-28, loaded at systems/sytem_CAR.py:113-125).
+ * host_blob: fp32, per net in order {model_u_w1 (NOUT=48), model_u_w2 (NOUT=24)}:
+ *     W1[128][4] b1[128] W2[128][128] b2[128] W3[NOUT][128] b3[NOUT]       (torch Linear.weight layout [out][in])
+ */
+int dp_controller_create(const float *host_blob, size_t n_floats, int device, dp_controller **out);
+void dp_controller_destroy(dp_controller *c);
+
+/*
+ * Fused closed-loop rollout with Liouville density.  Replaces the Python loop of
+ * ControlAffineSystem.compute_density (systems/ControlAffineSystem.py:409-463), i.e. per step
+ * get_next_rholog/get_next_rho (:136-157) -> divf_func (:116) -> dfdx_func (:93) -> dudx_func (:69) -> jacobian
+ * (systems/utils.py:5) and get_next_x (:124) -> f_func (:43) -> Controller.__call__ (systems/sytem_CAR.py:25).
+ *
+ *   xe0   dev [N][5]      initial error states           xref dev [5][T+1]     uref dev [2][T]
+ *   rho0  dev [N] or NULL initial (log-)density (NULL: 0 for log, 1 for linear)
+ *   stride               store every `stride`-th step (t = 0, stride, ...), Ts = T/stride + 1 slots
+ *   x_out   dev [Ts][5][ldn] (or [Ts][2][ldn] with DP_XY_ONLY) or NULL
+ *   rho_out dev [Ts][ldn] or NULL
+ *   clip_margin dev [N] or NULL: min over (step, input) of | |u_raw| - 3 |  (distance to the actuator clip; audit)
+ *   status  dev int[2] or NULL: [0] |= 1 if a density was clamped, [1] |= 1 if a NaN was replaced (DP_CUT)
+ */
+int dp_rollout(const dp_controller *c, const float *xe0, const float *xref, const float *uref, const float *rho0,
+               float dt, int64_t N, int T, unsigned flags, int stride, float *x_out, float *rho_out, int64_t ldn,
+               float *clip_margin, int *status, void *stream);
+
+/* Same with HOST buffers (x_out/rho_out host, ld = N); status is a host int[2].  Copies are part of the call. */
+int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const float *uref, const float *rho0,
+                    float dt, int64_t N, int T, unsigned flags, int stride, float *x_out, float *rho_out,
+                    float *clip_margin, int *status);
+
+/*
+ * Single-step API: u_func (:26), f_func (:43), dudx_func (:69), dfdx_func (:93), divf_func (:116) of
+ * systems/ControlAffineSystem.py for N states sharing one (xref, uref).
+ *   x dev [N][5]; xref5 dev [5]; uref2 dev [2]
+ *   outputs (each may be NULL): u_raw [N][2], u [N][2] (clipped), dudx [N][2][5] (clip mask applied, as autograd
+ *   of torch.clip gives), f [N][5], div [N]
+ */
+int dp_step(const dp_controller *c, const float *x, const float *xref5, const float *uref2, int64_t N, float *u_raw,
+            float *u, float *dudx, float *f, float *div, void *stream);
+
+/* ---- grid geometry (hyperparams.py:124,154-155) ----------------------------------------------------------- */
+typedef struct dp_grid_geom {
+    float x_min, x_max, y_min, y_max; /* args.environment_size */
+    int gx, gy;                       /* args.grid_size        */
+} dp_grid_geom;
+
+/* pos2gridpos (motion_planning/utils.py:70-97): round_half_even(((p - lo)/(hi - lo))*(G-1) + 0.001), fp32 op for op.
+ * px, py dev [n] -> ix, iy dev int32 [n] (either pair may be NULL).  clamp_hi < 0: no clamp, else clamp to [0,clamp] */
+int dp_pos2gridpos(const dp_grid_geom *g, const float *px, const float *py, int64_t n, int32_t *ix, int32_t *iy,
+                   int clamp_hi_x, int clamp_hi_y, void *stream);
+/* gridpos2pos (motion_planning/utils.py:100-116) on float grid positions */
+int dp_gridpos2pos(const dp_grid_geom *g, const float *gx, const float *gy, int64_t n, float *px, float *py,
+                   void *stream);
+
+/*
+ * Environment grids (motion_planning/simulation_objects.py:29-44,77-94): grid, grid_gradientX, grid_gradientY,
+ * each (G0, G1, Tg) fp32 with time innermost (the reference layout).  `on_device` says where the three inputs live.
+ * They are repacked once into a time-major float4 table {p, gX, gY, 0}[t][ix][iy] so that one 16-byte gather serves
+ * a collision-cost evaluation.
+ */
+int dp_env_create(const dp_grid_geom *g, int Tg, const float *grid, const float *gradx, const float *grady,
+                  int on_device, int device, dp_env **out);
+void dp_env_destroy(dp_env *e);
+
+/*
+ * Collision cost, forward and analytic backward: MotionPlanner.get_cost_coll (motion_planning/MotionPlanner.py:192-224)
+ * and MotionPlannerGrad.get_cost_coll_initialize (motion_planning/MotionPlannerGrad.py:309-336).
+ *   x, y   dev, element (n, t) at x[n*sx_n + t*sx_t] (strides in elements; covers both the reference (N,5,Ts) layout
+ *          and this library's [t][d][n] layout)
+ *   rho    dev (same addressing with sr_n, sr_t) or NULL (=> weights 1, the *_initialize variant)
+ *   Ts     number of time slices evaluated (slice t uses env time index t)
+ *   cost_slices   dev double[Ts] or NULL: per-slice sum (or per-slice max with get_max)
+ *   cost_samples  dev double[N]  or NULL: per-sample sum over slices (get_cost_coll_initialize)
+ *   gx, gy, grho  dev or NULL: d(sum cost)/dx, /dy, /drho, same addressing as x / rho (written, not accumulated)
+ *   total  dev double[1] or NULL: sum over slices of cost_slices (needs cost_slices workspace inside; deterministic)
+ */
+int dp_cost_coll(const dp_env *e, const float *x, const float *y, int64_t sx_n, int64_t sx_t, const float *rho,
+                 int64_t sr_n, int64_t sr_t, int64_t N, int Ts, int get_max, double *cost_slices, double *cost_samples,
+                 float *gx, float *gy, float *grho, int64_t sg_n, int64_t sg_t, double *total, void *stream);
+
+/*
+ * Deterministic 2-D binning with integer accumulation (one time slice per call, or Ts slices with strides).
+ * mode 0: occupancy-grid cells, pred2grid (motion_planning/utils.py:255-280): cell = clamp(pos2gridpos(p), 0, G)
+ *         (clamp to G, not G-1, as the reference does); grid arrays are (gx+1) x (gy+1) per slice.
+ * mode 1: uniform bins like np.histogramdd (systems/utils.py:105-129): bins (bx, by) over [lo, hi], right edge
+ *         inclusive, samples outside dropped; grid arrays are bx x by per slice.
+ *   w      dev weights (same addressing as x with sw_n, sw_t) or NULL (weight 1)
+ *   mass   dev int64 [Ts][cells]: sum of llrint(w * 2^mass_scale_log2)  (accumulated with atomics: exact, order-free)
+ *   count  dev int32 [Ts][cells]
+ *   occ, occ_cost: if occ != NULL (dev float [cells][To] reference-layout occupancy grid is NOT used here; see
+ *          dp_cost_coll) -- reserved, pass NULL.
+ */
+typedef struct dp_bin_spec {
+    int mode;            /* 0 grid cells, 1 uniform bins */
+    dp_grid_geom geom;   /* mode 0 */
+    double lo_x, hi_x, lo_y, hi_y; /* mode 1 */
+    int bx, by;          /* mode 1 */
+    int mass_scale_log2; /* fixed-point scale of the mass accumulator */
+} dp_bin_spec;
+
+int dp_bin2d(const dp_bin_spec *spec, const float *x, const float *y, int64_t sx_n, int64_t sx_t, const float *w,
+             int64_t sw_n, int64_t sw_t, int64_t N, int Ts, long long *mass, int *count, void *stream);
+
+/*
+ * Density normaliser of EgoVehicle.predict_density (motion_planning/simulation_objects.py:295-299), per time slot:
+ *     rho[t][n] = exp(l[t][n] - max_n l[t][.]) * rho0[n] / sum_n(...)
+ * rholog dev [Ts][ldn] -> rho dev [Ts][ldn] (may alias).  Optional lmax / lsum dev float[Ts] receive the per-slot
+ * max and (unnormalised) sum so a multi-GPU caller can merge them with an allreduce and call dp_normalize_apply.
+ */
+int dp_normalize_stats(const float *rholog, const float *rho0, int64_t N, int Ts, int64_t ldn, float *lmax,
+                       double *lsum_at_max, void *stream);
+int dp_normalize_apply(const float *rholog, const float *rho0, int64_t N, int Ts, int64_t ldn, const float *lmax,
+                       const double *lsum, float *rho, void *stream);
+
+/* FP32 FFMA peak probe (measures the CUDA-core roofline the fp32 kernel is bounded by); returns TFLOP/s in *tflops */
+int dp_probe_ffma_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DENSITY_PLANNER_B200_H */

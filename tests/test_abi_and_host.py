@@ -1,0 +1,98 @@
+"""CPU suite: the C-ABI library loads and exports every symbol the header declares; host-side logic of the package
+(weight packing, reference sampling in the reference's RNG order, loud failure without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "density_planner_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(dp):
+    from density_planner_b200 import _lib
+    names = header_functions()
+    assert len(names) >= 15
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), "missing export %s" % n
+    # the binding table covers the header too
+    assert set(names) == set(_lib.EXPORTS)
+    assert dp.lib().dp_abi_version() == 1
+
+
+def test_library_is_sm100a_native():
+    """The shipped .so carries sm_100a SASS (no PTX-JIT path, no other arch)."""
+    import subprocess
+    from density_planner_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(?!100a)\d+", out)
+
+
+def test_weight_packing_matches_oracle(oracle, blob):
+    from density_planner_b200.controller import load_blob, random_blob
+    b = load_blob()
+    assert b.dtype == np.float32 and b.size == 43592
+    assert (b == blob).all()
+    r = random_blob(3)
+    assert r.size == 43592 and np.isfinite(r).all()
+
+
+def test_reference_sampling_rng_order(dp, args):
+    """get_valid_ref + sample_xe0 consume the torch RNG exactly like the reference (golden minted with seed 0)."""
+    g = golden("rollout_cfg1.npz")
+    car = dp.Car(args)
+    torch.manual_seed(0)
+    up, uref, xref = car.get_valid_ref(args)
+    xe0 = car.sample_xe0(20)
+    assert (up.numpy() == g["up"]).all()
+    assert (uref[0].numpy() == g["uref"]).all()
+    assert (xref[0].numpy() == g["xref"]).all()
+    assert (xe0[:, :, 0].numpy() == g["xe0"]).all()
+
+
+def test_up2ref_and_cut(dp, args):
+    car = dp.Car(args)
+    up = torch.tensor([[[1.0, -1, 0.5, 0, 0, 2, -2, 0, 1, 0], [0.5, 0, 0, -0.5, 0, 0, 0.3, 0, 0, 0]]])
+    xref0 = torch.tensor([0, -28, 1.5, 3, 0.0]).reshape(1, 5, 1)
+    uref, xref = car.up2ref_traj(xref0, up, args, short=True)
+    assert uref.shape == (1, 2, 100) and xref.shape == (1, 5, 101)
+    ur_l, xr_l = car.up2ref_traj(xref0, up, args, short=False)
+    assert ur_l.shape == (1, 2, 1000) and xr_l.shape == (1, 5, 1001)
+    # Euler step of the bicycle model by hand
+    x1 = xref0[0, :, 0] + torch.tensor([3 * np.cos(1.5), 3 * np.sin(1.5), 1.0, 0.5, 0.0]) * 0.01
+    assert torch.allclose(xr_l[0, :, 1], x1.float(), atol=1e-6)
+    # cut: leave the admissible box in v
+    xr_bad = xr_l.clone()
+    xr_bad[0, 3, 500:] = 11.0
+    xc, uc = car.cut_xref_traj(xr_bad, ur_l)
+    assert xc.shape[2] == 500 and uc.shape[2] == 499
+
+
+def test_no_cpu_fallback(dp, args):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    car = dp.Car(args)
+    with pytest.raises(dp.DensityPlannerError):
+        car.compute_density(car.sample_xe0(4), torch.zeros(1, 5, 11), torch.zeros(1, 2, 10), 0.01)
+    with pytest.raises(dp.DensityPlannerError):
+        dp.pos2gridpos(args, pos_x=torch.zeros(3))
+
+
+def test_product_does_not_import_oracle():
+    """The product package must not reach into oracle/ (checked on the sources)."""
+    pkg = os.path.join(ROOT, "density_planner_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                s = open(os.path.join(dirpath, f)).read()
+                assert "dp_oracle" not in s and "ref_harness" not in s, f

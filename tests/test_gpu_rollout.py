@@ -1,0 +1,176 @@
+"""GPU parity tests of the fused rollout kernel(s) and the single-step API, through the package (which calls the C ABI).
+Checked against (1) the golden vectors of the unmodified reference, (2) the CPU oracle on fresh seeded inputs,
+(3) size-independent properties at the full BASELINE size."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, assert_states_close, assert_rho_close, FLIP_MARGIN
+
+pytestmark = pytest.mark.gpu
+
+IMPLS = ["ffma"]
+
+
+def _tc_available():
+    return False
+
+
+def _run(car, g, impl, stride=1, device="cuda", **kw):
+    dev = torch.device(device)
+    xe0 = torch.from_numpy(g["xe0"]).unsqueeze(-1).to(dev)
+    xref = torch.from_numpy(g["xref"]).unsqueeze(0).to(dev)
+    uref = torch.from_numpy(g["uref"]).unsqueeze(0).to(dev)
+    out = car.compute_density(xe0, xref, uref, float(g["dt"]), stride=stride, impl=impl, return_margin=True, **kw)
+    xe, rho, margin = out
+    return (xe.cpu().numpy(), None if rho is None else rho[:, 0, :].cpu().numpy(), margin.cpu().numpy())
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", ["rollout_cfg1", "rollout_n2000_t300", "rollout_n4000_t100"])
+def test_rollout_vs_reference_golden(car, impl, name):
+    g = golden(name + ".npz")
+    stride = int(g["stride"]) if "stride" in g.files else 1
+    xe, rho, margin = _run(car, g, impl, stride=stride, cutting=True, log_density=True)
+    assert xe.shape == g["xe_traj"].shape and rho.shape == g["rholog_traj"].shape
+    assert_states_close(xe, g["xe_traj"], g["xref"][:, ::stride], name)
+    assert_rho_close(rho, g["rholog_traj"], np.minimum(margin, g["clip_margin"]), name)
+    assert np.abs(margin - g["clip_margin"]).max() < 1e-3
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_rollout_host_buffers_and_strided_store(car, impl):
+    """CPU tensors in / CPU tensors out (dp_rollout_host), and stride>1 equals subsampling of stride 1."""
+    g = golden("rollout_n4000_t100.npz")
+    xe_s, rho_s, _ = _run(car, g, impl, stride=10, device="cpu", cutting=True, log_density=True)
+    xe_f, rho_f, _ = _run(car, g, impl, stride=1, device="cuda", cutting=True, log_density=True)
+    assert (xe_s == xe_f[:, :, ::10]).all() and (rho_s == rho_f[:, ::10]).all()
+    assert_states_close(xe_s, g["xe_traj"], g["xref"][:, ::10], "host")
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_rollout_modes(car, impl):
+    g = golden("rollout_modes.npz")
+    s = int(g["stride"])
+    xref_s = g["xref"][:, ::s]
+    rho0 = torch.from_numpy(g["rho0"]).reshape(-1, 1, 1).cuda()
+    xe, rho, _ = _run(car, g, impl, stride=s, rho0=rho0, cutting=True, log_density=False)
+    assert_states_close(xe, g["xe_lin"], xref_s, "linear")
+    assert np.allclose(rho, g["rho_lin"], rtol=1e-3, atol=1e-6)
+    xe, rho, _ = _run(car, g, impl, stride=s, cutting=False, log_density=True)
+    assert_rho_close(rho, g["rholog"], None, "log, no cutting")
+    xe, rho, _ = _run(car, g, impl, stride=s, compute_density=False)
+    assert rho is None
+    assert_states_close(xe, g["xe_nodens"], xref_s, "no density")
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("N,T", [(1, 7), (31, 33), (33, 1), (1000, 50), (4737, 20)])
+def test_rollout_vs_oracle_ragged(car, oracle, blob, args, impl, N, T):
+    """Ragged sizes (tail tiles, single sample, single step) against the CPU oracle on seeded inputs."""
+    torch.manual_seed(100 + N)
+    up, uref, xref = car.get_valid_ref(args)
+    uref, xref = uref[:, :, :T], xref[:, :, :T + 1]
+    xe0 = car.sample_xe0(N)
+    xe, rho, margin = car.compute_density(xe0.cuda(), xref, uref, args.dt_sim, log_density=True, impl=impl,
+                                          return_margin=True)
+    o_xe, o_rho, o_m, _ = oracle.rollout(blob, xe0[:, :, 0].numpy(), xref[0].numpy(), uref[0].numpy(), args.dt_sim,
+                                         want_margin=True)
+    assert_states_close(xe.cpu().numpy(), o_xe, xref[0].numpy(), "N=%d T=%d" % (N, T))
+    assert_rho_close(rho[:, 0, :].cpu().numpy(), o_rho, np.minimum(margin.cpu().numpy(), o_m), "N=%d T=%d" % (N, T))
+
+
+def test_rollout_empty(car, args):
+    xe, rho = car.compute_density(torch.zeros(0, 5, 1).cuda(), torch.zeros(1, 5, 11), torch.zeros(1, 2, 10), 0.01,
+                                  log_density=True)
+    assert xe.shape == (0, 5, 11) and rho.shape == (0, 1, 11)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_cutting_clamps_and_reports(car, args, impl, capsys):
+    """Densities above 1e30 are clamped with the reference's message (ControlAffineSystem.py:451-462)."""
+    torch.manual_seed(7)
+    up, uref, xref = car.get_valid_ref(args)
+    uref, xref = uref[:, :, :5], xref[:, :, :6]
+    xe0 = car.sample_xe0(64).cuda()
+    rho0 = torch.full((64, 1, 1), 3e30).cuda()
+    xe, rho = car.compute_density(xe0, xref, uref, args.dt_sim, rho0=rho0, cutting=True, log_density=True, impl=impl)
+    assert float(rho.max()) <= 1e30
+    assert "clamp rho_traj to 1e30 (log density)" in capsys.readouterr().out
+    xe, rho = car.compute_density(xe0, xref, uref, args.dt_sim, rho0=rho0, cutting=False, log_density=True, impl=impl)
+    assert float(rho.max()) > 1e30
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_full_size_properties(car, oracle, blob, args, impl):
+    """BASELINE config 2 size (1M samples x 100 steps): (a) permutation equivariance / tile independence: the same
+    sample gives the same trajectory wherever it sits in the batch; (b) a strided spot check against the oracle;
+    (c) density of a duplicated sample is identical (determinism)."""
+    N, T = 1_000_000, 100
+    torch.manual_seed(11)
+    up, uref, xref = car.get_valid_ref(args)
+    uref, xref = uref[:, :, :T], xref[:, :, :T + 1]
+    base = car.sample_xe0(4096)
+    idx = torch.randint(0, 4096, (N,))
+    xe0 = base[idx].cuda()
+    xe, rho = car.compute_density(xe0, xref, uref, args.dt_sim, log_density=True, stride=10, impl=impl)
+    # (a)+(c): all copies of base sample k are bit-identical
+    xe_last = xe[:, :, -1]
+    rho_last = rho[:, 0, -1]
+    first = torch.full((4096,), -1, dtype=torch.long)
+    order = torch.arange(N - 1, -1, -1)
+    first[idx[order]] = order
+    ref_x = xe_last[first.cuda()][idx.cuda()]
+    ref_r = rho_last[first.cuda()][idx.cuda()]
+    assert bool((ref_x == xe_last).all()) and bool((ref_r == rho_last).all())
+    # (b) oracle spot check on the 4096 base samples
+    o_xe, o_rho, o_m, _ = oracle.rollout(blob, base[:, :, 0].numpy(), xref[0].numpy(), uref[0].numpy(), args.dt_sim,
+                                         stride=10, want_margin=True)
+    got_x = xe[first.cuda()].cpu().numpy()
+    got_r = rho[first.cuda()][:, 0, :].cpu().numpy()
+    assert_states_close(got_x, o_xe, xref[0].numpy()[:, ::10], "1M spot check")
+    assert_rho_close(got_r, o_rho, o_m, "1M spot check")
+
+
+def test_step_api_vs_reference_golden(car):
+    g = golden("step_api.npz")
+    x = torch.from_numpy(g["x"]).unsqueeze(-1)
+    xref = torch.from_numpy(g["xref"]).reshape(1, 5, 1)
+    uref = torch.from_numpy(g["uref"]).reshape(1, 2, 1)
+    dt = float(g["dt"])
+    u = car.u_func(x, xref, uref)
+    assert u.shape == (4096, 2, 1) and u.device.type == "cpu"
+    assert np.allclose(u[:, :, 0].numpy(), g["u"], rtol=1e-5, atol=2e-5)
+    f = car.f_func(x.cuda(), xref, uref)
+    assert f.is_cuda and np.allclose(f[:, :, 0].cpu().numpy(), g["f"], rtol=1e-5, atol=2e-5)
+    safe = (np.abs(np.abs(g["u_raw"]) - 3) > 1e-4).all(axis=1)
+    dudx = car.dudx_func(x, xref, uref).numpy()
+    assert dudx.shape == (4096, 2, 5)
+    assert np.abs(dudx[safe] - g["dudx"][safe]).max() < 1e-4 * np.abs(g["dudx"]).max()
+    dfdx = car.dfdx_func(x, xref, uref).numpy()
+    assert np.abs(dfdx[safe] - g["dfdx"][safe]).max() < 1e-4 * np.abs(g["dfdx"]).max()
+    div = car.divf_func(x, xref, uref).numpy()
+    assert np.abs(div[safe] - g["div"][safe]).max() < 1e-4 * np.abs(g["div"]).max()
+    xn = car.get_next_x(x, xref, uref, dt)
+    assert np.allclose(xn[:, :, 0].numpy(), g["x_next"], rtol=1e-6, atol=2e-6)
+    rho = torch.from_numpy(g["rho"])
+    rn = car.get_next_rho(x, xref, uref, rho, dt).numpy()
+    rln = car.get_next_rholog(x, xref, uref, rho, dt).numpy()
+    assert np.allclose(rn[safe], g["rho_next"][safe], rtol=1e-4, atol=1e-5)
+    assert np.allclose(rln[safe], g["rholog_next"][safe], rtol=1e-4, atol=1e-5)
+
+
+def test_compute_data_matches_reference_golden(dp, car, args):
+    """data_generation/compute_rawdata.py:9 with seed 5: same references, same samples, same time indices."""
+    g = golden("compute_data.npz")
+    torch.manual_seed(5)
+    res = dp.compute_data([1, 2], 20, car, args, samples_t=10, save=False, plot=False)
+    assert len(res) == 2
+    for i, r in enumerate(res):
+        assert (r["u_params"].numpy() == g["r%d_u_params" % i]).all()
+        assert (r["xref0"].numpy() == g["r%d_xref0" % i]).all()
+        assert (r["t"].numpy() == g["r%d_t" % i]).all()
+        assert (r["xe0"].numpy() == g["r%d_xe0" % i]).all()
+        assert np.abs(r["xe_traj"].numpy() - g["r%d_xe_traj" % i]).max() < 1e-4
+        ref = g["r%d_rholog_traj" % i]
+        assert np.abs(r["rholog_traj"].numpy() - ref).max() < 1e-3 * np.abs(ref).max() + 1e-4
