@@ -199,6 +199,10 @@ class ControlAffineSystem:
         flags |= {None: _lib.DP_IMPL_DEFAULT, "ffma": _lib.DP_IMPL_FFMA, "tc": _lib.DP_IMPL_TC}[impl]
         Ts = T // stride + 1
         status = None
+        if N == 0:
+            xe_traj = torch.empty((0, 5, Ts), dtype=torch.float32, device=out_dev)
+            rho_traj = torch.empty((0, 1, Ts), dtype=torch.float32, device=out_dev) if compute_density else None
+            return (xe_traj, rho_traj, torch.empty(0, device=out_dev)) if return_margin else (xe_traj, rho_traj)
         if out_dev.type == "cuda":
             xe0_d = _f32(xe0.reshape(N, 5), dev)
             xref_d = _f32(xref_traj.reshape(5, T + 1), dev)

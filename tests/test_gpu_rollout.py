@@ -95,10 +95,10 @@ def test_cutting_clamps_and_reports(car, args, impl, capsys):
     xe0 = car.sample_xe0(64).cuda()
     rho0 = torch.full((64, 1, 1), 3e30).cuda()
     xe, rho = car.compute_density(xe0, xref, uref, args.dt_sim, rho0=rho0, cutting=True, log_density=True, impl=impl)
-    assert float(rho.max()) <= 1e30
+    assert float(rho.max()) <= float(np.float32(1e30))
     assert "clamp rho_traj to 1e30 (log density)" in capsys.readouterr().out
     xe, rho = car.compute_density(xe0, xref, uref, args.dt_sim, rho0=rho0, cutting=False, log_density=True, impl=impl)
-    assert float(rho.max()) > 1e30
+    assert float(rho.max()) > 2e30
 
 
 @pytest.mark.parametrize("impl", IMPLS)
