@@ -170,6 +170,12 @@ int dp_normalize_stats(const float *rholog, const float *rho0, int64_t N, int Ts
 int dp_normalize_apply(const float *rholog, const float *rho0, int64_t N, int Ts, int64_t ldn, const float *lmax,
                        const double *lsum, float *rho, void *stream);
 
+/* Diagnostic: one 128 x n x 128 product through the TMEM-operand tcgen05.mma path of the tensor-core rollout
+ * (split-precision fp16 operands).  A host fp32 [128][128], W host fp32 [n_valid][128] zero-padded to n rows
+ * (n in {128, 48, 32}), mode 0 = value path (3 products), 1 = tangent path (2 products); D host fp32 [128][n]
+ * receives A * (scale * W)^T. */
+int dp_tc_selftest(int device, const float *A, const float *W, int n_valid, int n, int mode, float scale, float *D);
+
 /* FP32 FFMA peak probe (measures the CUDA-core roofline the fp32 kernel is bounded by); returns TFLOP/s in *tflops */
 int dp_probe_ffma_peak(int device, double *tflops);
 

@@ -9,11 +9,40 @@ from conftest import golden, assert_states_close, assert_rho_close, FLIP_MARGIN
 
 pytestmark = pytest.mark.gpu
 
-IMPLS = ["ffma"]
+IMPLS = ["ffma", "tc"]
 
 
-def _tc_available():
-    return False
+def _split16(x):
+    hi = x.astype(np.float16).astype(np.float32)
+    return hi, (x - hi).astype(np.float16).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,n_valid", [(128, 128), (48, 48), (32, 24)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tc_mma_building_block(dp, n, n_valid, mode):
+    """One 128 x n x 128 product through the TMEM-operand tcgen05.mma path against a numpy emulation of the split
+    fp16 operands (value path: 3 products, fp32-level; tangent path: fp16 activations x hi+lo weights)."""
+    import ctypes
+    L = dp.lib()
+    rs = np.random.RandomState(n + mode)
+    A = rs.uniform(-1, 1, (128, 128)).astype(np.float32)
+    W = rs.uniform(-0.25, 0.25, (n_valid, 128)).astype(np.float32)
+    D = np.zeros((128, n), np.float32)
+    rc = L.dp_tc_selftest(0, A.ctypes.data_as(ctypes.c_void_p), W.ctypes.data_as(ctypes.c_void_p), n_valid, n, mode, 16.0,
+                          D.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    Ah, Al = _split16(A)
+    Wp = np.zeros((n, 128), np.float32)
+    Wp[:n_valid] = W * 16
+    Wh, Wl = _split16(Wp)
+    ref = Ah.astype(np.float64) @ (Wh + Wl).astype(np.float64).T
+    if mode == 0:
+        ref += Al.astype(np.float64) @ Wh.astype(np.float64).T
+    assert np.abs(D - ref).max() < 2e-6 * np.abs(ref).max() + 1e-5
+    if mode == 0:  # three products reproduce the fp32 product to ~22 bits
+        exact = A.astype(np.float64) @ Wp.astype(np.float64).T
+        assert np.abs(D - exact).max() < 2e-6 * np.abs(exact).max() + 1e-5
+    assert (D[:, n_valid:] == 0).all()
 
 
 def _run(car, g, impl, stride=1, device="cuda", **kw):
