@@ -97,8 +97,9 @@ int dp_rollout(const dp_controller *c, const float *xe0, const float *xref, cons
     p.dt = dt; p.N = N; p.T = T; p.flags = flags; p.stride = stride; p.Ts = T / stride + 1;
     p.x_out = x_out; p.rho_out = rho_out; p.ldn = ldn; p.clip_margin = clip_margin; p.status = status;
     const unsigned impl = flags & DP_IMPL_MASK;
-    if (impl == DP_IMPL_TC) return dp_launch_rollout_tc(c, p, (cudaStream_t)stream);
-    if (impl == DP_IMPL_FFMA || impl == DP_IMPL_DEFAULT) return dp_launch_rollout_ffma(c, p, (cudaStream_t)stream);
+    // default = the tcgen05 kernel (fp32-level value path); DP_IMPL_FFMA selects the all-fp32 CUDA-core kernel
+    if (impl == DP_IMPL_TC || impl == DP_IMPL_DEFAULT) return dp_launch_rollout_tc(c, p, (cudaStream_t)stream);
+    if (impl == DP_IMPL_FFMA) return dp_launch_rollout_ffma(c, p, (cudaStream_t)stream);
     dp_set_error("dp_rollout: unknown implementation selector 0x%x", impl);
     return 2;
 }
