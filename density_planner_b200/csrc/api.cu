@@ -80,6 +80,13 @@ void dp_controller_destroy(dp_controller *c) {
     cudaFree(c->d_small);
     cudaFree(c->ws.ptr);
     if (c->host_stream) cudaStreamDestroy(c->host_stream);
+    if (c->copy_stream) {
+        cudaStreamDestroy(c->copy_stream);
+        for (int b = 0; b < 2; ++b) {
+            cudaEventDestroy(c->ev_done[b]);
+            cudaEventDestroy(c->ev_copied[b]);
+        }
+    }
     delete c;
 }
 
@@ -123,37 +130,68 @@ int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const
     DeviceGuard guard(c->device);
     const int Ts = T / stride + 1;
     const int nd = (flags & DP_XY_ONLY) ? 2 : 5;
+    // Samples are processed in chunks of whole waves (128 samples x #SMs x 8); the device->host copy of chunk k overlaps
+    // the rollout of chunk k+1 (two output buffers, a compute stream and a copy stream).
+    const int64_t wave = 128LL * c->num_sms;
+    int64_t chunk = 8 * wave;
+    if (chunk > N) chunk = N;
+    const int64_t nchunks = (N + chunk - 1) / chunk;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t b_xe0 = al(sizeof(float) * N * 5), b_xref = al(sizeof(float) * 5 * (T + 1)), b_uref = al(sizeof(float) * 2 * (T > 0 ? T : 1));
+    const size_t b_xe0 = al(sizeof(float) * N * 5), b_xref = al(sizeof(float) * 5 * (T + 1)),
+                 b_uref = al(sizeof(float) * 2 * (T > 0 ? T : 1));
     const size_t b_rho0 = rho0 ? al(sizeof(float) * N) : 0;
-    const size_t b_x = x_out ? al(sizeof(float) * (size_t)Ts * nd * N) : 0;
-    const size_t b_rho = rho_out ? al(sizeof(float) * (size_t)Ts * N) : 0;
+    const size_t b_x = x_out ? al(sizeof(float) * (size_t)Ts * nd * chunk) : 0;
+    const size_t b_rho = rho_out ? al(sizeof(float) * (size_t)Ts * chunk) : 0;
     const size_t b_m = clip_margin ? al(sizeof(float) * N) : 0;
     const size_t b_st = 256;
-    if (ws_reserve(c, b_xe0 + b_xref + b_uref + b_rho0 + b_x + b_rho + b_m + b_st)) return 1;
+    if (ws_reserve(c, b_xe0 + b_xref + b_uref + b_rho0 + 2 * (b_x + b_rho) + b_m + b_st)) return 1;
     char *base = (char *)c->ws.ptr;
     float *d_xe0 = (float *)base; base += b_xe0;
     float *d_xref = (float *)base; base += b_xref;
     float *d_uref = (float *)base; base += b_uref;
     float *d_rho0 = rho0 ? (float *)base : nullptr; base += b_rho0;
-    float *d_x = x_out ? (float *)base : nullptr; base += b_x;
-    float *d_rho = rho_out ? (float *)base : nullptr; base += b_rho;
+    float *d_x[2] = {nullptr, nullptr}, *d_rho[2] = {nullptr, nullptr};
+    for (int b = 0; b < 2; ++b) {
+        d_x[b] = x_out ? (float *)base : nullptr; base += b_x;
+        d_rho[b] = rho_out ? (float *)base : nullptr; base += b_rho;
+    }
     float *d_m = clip_margin ? (float *)base : nullptr; base += b_m;
     int *d_st = (int *)base;
-    cudaStream_t st = c->host_stream;
-    DP_CUDA(cudaMemcpyAsync(d_xe0, xe0, sizeof(float) * N * 5, cudaMemcpyHostToDevice, st));
+    if (!c->copy_stream) {
+        DP_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            DP_CUDA(cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming));
+            DP_CUDA(cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t st = c->host_stream, cp = c->copy_stream;
     DP_CUDA(cudaMemcpyAsync(d_xref, xref, sizeof(float) * 5 * (T + 1), cudaMemcpyHostToDevice, st));
     if (T > 0) DP_CUDA(cudaMemcpyAsync(d_uref, uref, sizeof(float) * 2 * T, cudaMemcpyHostToDevice, st));
-    if (rho0) DP_CUDA(cudaMemcpyAsync(d_rho0, rho0, sizeof(float) * N, cudaMemcpyHostToDevice, st));
     DP_CUDA(cudaMemsetAsync(d_st, 0, 2 * sizeof(int), st));
-    int rc = dp_rollout(c, d_xe0, d_xref, d_uref, d_rho0, dt, N, T, flags, stride, d_x, d_rho, N, d_m, d_st, st);
-    if (rc) return rc;
-    if (x_out) DP_CUDA(cudaMemcpyAsync(x_out, d_x, sizeof(float) * (size_t)Ts * nd * N, cudaMemcpyDeviceToHost, st));
-    if (rho_out) DP_CUDA(cudaMemcpyAsync(rho_out, d_rho, sizeof(float) * (size_t)Ts * N, cudaMemcpyDeviceToHost, st));
-    if (clip_margin) DP_CUDA(cudaMemcpyAsync(clip_margin, d_m, sizeof(float) * N, cudaMemcpyDeviceToHost, st));
+    for (int64_t k = 0; k < nchunks; ++k) {
+        const int64_t off = k * chunk, n = (off + chunk <= N) ? chunk : N - off;
+        const int b = (int)(k & 1);
+        DP_CUDA(cudaMemcpyAsync(d_xe0 + off * 5, xe0 + off * 5, sizeof(float) * n * 5, cudaMemcpyHostToDevice, st));
+        if (rho0) DP_CUDA(cudaMemcpyAsync(d_rho0 + off, rho0 + off, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+        if (k >= 2) DP_CUDA(cudaStreamWaitEvent(st, c->ev_copied[b], 0));  // buffer b has been drained to the host
+        int rc = dp_rollout(c, d_xe0 + off * 5, d_xref, d_uref, rho0 ? d_rho0 + off : nullptr, dt, n, T, flags, stride, d_x[b],
+                            d_rho[b], chunk, d_m ? d_m + off : nullptr, d_st, st);
+        if (rc) return rc;
+        DP_CUDA(cudaEventRecord(c->ev_done[b], st));
+        DP_CUDA(cudaStreamWaitEvent(cp, c->ev_done[b], 0));
+        if (x_out)
+            DP_CUDA(cudaMemcpy2DAsync(x_out + off, sizeof(float) * N, d_x[b], sizeof(float) * chunk, sizeof(float) * n,
+                                      (size_t)Ts * nd, cudaMemcpyDeviceToHost, cp));
+        if (rho_out)
+            DP_CUDA(cudaMemcpy2DAsync(rho_out + off, sizeof(float) * N, d_rho[b], sizeof(float) * chunk, sizeof(float) * n,
+                                      (size_t)Ts, cudaMemcpyDeviceToHost, cp));
+        DP_CUDA(cudaEventRecord(c->ev_copied[b], cp));
+    }
     int h_st[2] = {0, 0};
+    if (clip_margin) DP_CUDA(cudaMemcpyAsync(clip_margin, d_m, sizeof(float) * N, cudaMemcpyDeviceToHost, st));
     DP_CUDA(cudaMemcpyAsync(h_st, d_st, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     DP_CUDA(cudaStreamSynchronize(st));
+    DP_CUDA(cudaStreamSynchronize(cp));
     if (status) { status[0] = h_st[0]; status[1] = h_st[1]; }
     return 0;
 }

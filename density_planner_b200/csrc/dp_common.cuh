@@ -43,6 +43,8 @@ struct dp_controller {
     // grow-only device workspace + stream for the *_host entry points
     dp_workspace ws;
     cudaStream_t host_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 };
 
 struct dp_env {
