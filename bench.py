@@ -312,18 +312,31 @@ def main():
     del _w
     barrier()
     e2e_steps = max(1, min(opts.steps, 3))
-    t0 = time.perf_counter()
+    t_sum = 0.0
+    xe_traj = rho_traj = None
     for _ in range(e2e_steps):
+        xe_traj = rho_traj = None  # the caller has consumed and dropped the previous result
+        t0 = time.perf_counter()
         xe_traj, rho_traj = car.compute_density(xe0_cpu, xref, uref, args.dt_sim, log_density=True, cutting=True, impl=impl)
         _ = float(rho_traj[0, 0, -1])
-    t_e2e = (time.perf_counter() - t0) / e2e_steps
-    t_e2e = D.max_over_ranks(t_e2e, dev)
+        t_sum += time.perf_counter() - t0
+    t_e2e = D.max_over_ranks(t_sum / e2e_steps, dev)
+    # context for the e2e number: the raw pinned device->host copy rate of this box for the same byte count
+    probe_dev = torch.empty((T + 1) * 6 * N, dtype=torch.float32, device=dev)
+    probe_host = torch.empty((T + 1) * 6 * N, dtype=torch.float32, pin_memory=True)
+    probe_host.copy_(probe_dev)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    probe_host.copy_(probe_dev)
+    torch.cuda.synchronize(dev)
+    d2h_gbs = probe_dev.numel() * 4 / (time.perf_counter() - t0) / 1e9
+    del probe_dev, probe_host
     e2e = {"value": world * N * T / t_e2e, "unit": UNIT,
            "h2d_bytes_per_step": int(4 * (N * 5 + 5 * (T + 1) + 2 * T)),
            "d2h_bytes_per_step": int(4 * (T + 1) * 6 * N),
            "api": "Car.compute_density(xe0, xref_traj, uref_traj, dt, log_density=True) with CPU tensors "
                   "(dp_rollout_host: H2D + kernel + D2H of the full (N,5,T+1)+(N,1,T+1) trajectory)",
-           "ms_per_step": 1e3 * t_e2e}
+           "ms_per_step": 1e3 * t_e2e, "pinned_d2h_gbs_measured": d2h_gbs}
     del xe_traj, rho_traj
 
     # ---- collision cost / binning throughput on the stored slices (second half of the metric) ---------------------
