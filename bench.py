@@ -138,7 +138,7 @@ def cpu_oracle_rate(target_seconds=12.0):
     up, uref, xref = car.get_valid_ref(a)
     uref, xref = uref[0, :, :STEPS].numpy(), xref[0, :, :STEPS + 1].numpy()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = O.set_threads(cores)  # all host threads (torchrun exports OMP_NUM_THREADS=1 by default)
     n_probe = max(cores * 8, 64)
     xe0 = car.sample_xe0(n_probe)[:, :, 0].numpy()
     t0 = time.perf_counter()

@@ -324,3 +324,12 @@ void FN(dpo_rollout)(const float *blob, const real *xe0, const real *xref, const
 }
 
 int FN(dpo_sizeof_real)(void) { return (int)sizeof(real); }
+
+#ifdef _OPENMP
+#include <omp.h>
+/* number of OpenMP threads the rollout loops use (torchrun exports OMP_NUM_THREADS=1; the CPU arm overrides it) */
+int FN(dpo_set_threads)(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+#endif

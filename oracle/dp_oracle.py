@@ -43,6 +43,11 @@ def lib():
     return _LIB
 
 
+def set_threads(n):
+    """Set the OpenMP thread count of the C oracle; returns the count in effect."""
+    return int(lib().dpo_set_threads_f32(int(n)))
+
+
 def pack_weights(sd):
     """state_dict (numpy or torch values, keys of U_FUNC: model_u_w{1,2}.{0,2,4}.{weight,bias}) -> fp32 blob.
 
