@@ -102,7 +102,7 @@ int dp_rollout(const dp_controller *c, const float *xe0, const float *xref, cons
     p.big = c->d_big; p.small = c->d_small; p.tc = c->d_tc;
     p.xe0 = xe0; p.xref = xref; p.uref = uref; p.rho0 = rho0;
     p.dt = dt; p.N = N; p.T = T; p.flags = flags; p.stride = stride; p.Ts = T / stride + 1;
-    p.x_out = x_out; p.rho_out = rho_out; p.ldn = ldn; p.clip_margin = clip_margin; p.status = status;
+    p.x_out = x_out; p.rho_out = rho_out; p.ldn = ldn; p.clip_margin = clip_margin; p.status = status; p.trace = nullptr;
     const unsigned impl = flags & DP_IMPL_MASK;
     // default = the tcgen05 kernel (fp32-level value path); DP_IMPL_FFMA selects the all-fp32 CUDA-core kernel
     if (impl == DP_IMPL_TC || impl == DP_IMPL_DEFAULT) return dp_launch_rollout_tc(c, p, (cudaStream_t)stream);

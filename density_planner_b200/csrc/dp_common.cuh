@@ -104,6 +104,7 @@ struct RolloutParams {
     long long ldn;
     float *clip_margin;
     int *status;
+    unsigned long long *trace;  // optional in-kernel timeline (DP_TC_TRACE), normally null
 };
 
 int dp_launch_rollout_ffma(const dp_controller *c, const RolloutParams &p, cudaStream_t stream);

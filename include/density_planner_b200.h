@@ -176,6 +176,11 @@ int dp_normalize_apply(const float *rholog, const float *rho0, int64_t N, int Ts
  * receives A * (scale * W)^T. */
 int dp_tc_selftest(int device, const float *A, const float *W, int n_valid, int n, int mode, float scale, float *D);
 
+/* Diagnostic: cycles per tcgen05.mma (M=128, N=n, K=16, fp16 operands, fp32 accumulate) over 4*iters back-to-back
+ * instructions on one SM.  variant 0: A in TMEM + B no-swizzle (the rollout's configuration), 1: A in TMEM + B
+ * SWIZZLE_128B, 2: A and B in shared memory no swizzle, 3: both SWIZZLE_128B.  out[0] issue, out[1] completion. */
+int dp_tc_mma_bench(int device, int variant, int n, int iters, double *out);
+
 /* FP32 FFMA peak probe (measures the CUDA-core roofline the fp32 kernel is bounded by); returns TFLOP/s in *tflops */
 int dp_probe_ffma_peak(int device, double *tflops);
 
