@@ -1,0 +1,567 @@
+// K1 (tensor-core version, two independent tile pipelines per CTA): fused closed-loop rollout + Liouville density on
+// tcgen05 (sm_100a).
+//
+// Same math and the same split-precision fp16 operand scheme as rollout_tc.cu (reference:
+// systems/ControlAffineSystem.py:409-463 and the closed form of :69-122; controller systems/sytem_CAR.py:25-37,
+// data/trained_controller/model_CAR.py:19-28), but organised so that the tensor pipe and the CUDA cores overlap without a
+// hand-built software pipeline:
+//
+//   * one persistent CTA per SM, 512 threads = TWO GROUPS of 8 warps.  Each group owns its own 128-sample tile and its
+//     own half of TMEM (256 columns = two 128-column regions R0 / R1) and runs the per-net chain below on its own; while
+//     one group waits for its MMAs the other group's epilogue math fills the issue slots, and vice versa.
+//   * no MMA warp: after the group's named barrier, one elected thread of the group's first warp issues the group's
+//     tcgen05.mma batch and commits it to the group's mbarrier; everybody in the group then waits on that mbarrier.
+//   * chain for one (tile, net), RA / RD = the group's two regions (they swap roles from one chain to the next):
+//       L1    CUDA cores: h1 = tanh(W1 in + b1) -> RA (value operand hi/lo, 128 cols); layer-1 gates g1 in registers
+//       M1    D = W2 h1 (3 products)                                RA -> RD (128 fp32 accumulator columns)
+//       C1    per 16-feature chunk: drain RD, h2 = tanh(.), write h2 hi/lo IN PLACE of the drained accumulator chunk
+//             (RD becomes the layer-3 value operand); park g1 in RA[0:64) (its value operand is dead); keep g2 gates
+//       M4    layer-3 value outputs (48 / 32 cols)                  RD -> RA[64:112)
+//       R4    read the value outputs (controller matrices); tangent seeds g1*W1[:,theta], g1*W1[:,v] -> RD[0:64), RD[64:128)
+//       M2    d/dtheta through layer 2                              RD[0:64)   -> RA (128 cols)
+//       C2    drain RA, scale by g2 -> RD[0:64) in place of the seed
+//       M3/C3 the same for d/dv                                     RD[64:128) -> RA -> RD[64:128)
+//       M5+M6 layer-3 tangents                                      RD[0:64) -> RA[0:N3), RD[64:128) -> RA[N3:2 N3)
+//       R56   read the tangent outputs; head sums
+//     Every operand is overwritten only after the MMA batch that read it has been committed and waited for.
+//   * the epilogue math is packed fp32x2 (FFMA2 / FADD2) with pre-scaled biases: pre-activations arrive already
+//     multiplied by 2 log2(e), tanh = 1 - 2 / (1 + 2^y) with MUFU.EX2 + MUFU.RCP.
+//   * both threads of a sample (feature halves h = 0, 1) carry the sample state redundantly in registers, so the Euler
+//     step needs one exchange of four partial head sums through shared memory and no broadcast of the next input.
+#include <stdlib.h>
+
+#include <vector>
+
+#include "dp_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int GW = 8;             // warps per group
+constexpr int GT = GW * 32;       // threads per group
+constexpr int NGROUPS = 2;
+constexpr int NTHREADS = NGROUPS * GT;
+#ifndef DP_TANGENT_PRODUCTS
+#define DP_TANGENT_PRODUCTS 2     // 2: fp16 tangent activations x (hi + lo) weights; 1: hi weights only
+#endif
+constexpr int TANGENT_PRODUCTS = DP_TANGENT_PRODUCTS;
+
+// per-net fp32 block of the operand image (this kernel's own layout of the "small" section)
+constexpr int SP_W1P = 0;    // [64 pairs][8]: {wx_j, wx_j1, wy_j, wy_j1 | wz_j, wz_j1, ww_j, ww_j1} * 2 log2(e)
+constexpr int SP_B1P = 512;  // [128] b1 * 2 log2(e)
+constexpr int SP_B2P = 640;  // [128] b2 * 2 log2(e)
+constexpr int SP_B3 = 768;   // [64]
+constexpr int SP_C0H = 832;  // [64] half2 pairs of W1[:,0]  (tangent seed d/dtheta)
+constexpr int SP_C1H = 896;  // [64] half2 pairs of W1[:,1]  (tangent seed d/dv)
+static_assert(SP_C1H + 64 == SMALL_NET_FLOATS, "small block layout");
+
+// shared memory behind the image
+constexpr int OFF_Z = IMAGE_BYTES;                              // float [2 groups][36][128]: tz, A, B per z-row
+constexpr int OFF_PART = OFF_Z + NGROUPS * 36 * TILE * 4;       // float [2 groups][2 halves][4][128]
+constexpr int OFF_BAR = OFF_PART + NGROUPS * 2 * 4 * TILE * 4;  // 2 mbarriers + tmem pointer
+constexpr int SMEM_BYTES = OFF_BAR + 64;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+constexpr float C2SCALE = INV_WSCALE * TWO_LOG2E;        // accumulator (x16) -> 2 log2(e) * pre-activation
+constexpr float INV_S2 = INV_WSCALE * INV_WSCALE;        // layer-3 tangent accumulators carry both x16 factors
+
+struct Ctx {
+    uint32_t RA, RD;    // lane-0 TMEM addresses of the two regions (MMA operands / accumulators)
+    uint32_t ra, rd;    // the same with this warp's lane offset (tcgen05.ld / st)
+    uint32_t bar;       // the group's mbarrier
+    uint32_t sbase;     // shared-memory address of the image
+    int bar_id;         // the group's named barrier
+    int h;              // feature half of this thread
+    int s;              // sample within the tile
+    bool leader;        // first warp of the group: issues the MMAs
+    const float *small; // fp32 blocks of both nets
+    float *sZ;          // this group's [36][128]
+};
+
+__device__ __forceinline__ void group_sync(int bar_id) { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GT) : "memory"); }
+
+// all TMEM traffic of this thread is complete and ordered before the group barrier
+__device__ __forceinline__ void publish(const Ctx &c) {
+    wait_st();
+    fence_before();
+    group_sync(c.bar_id);
+}
+__device__ __forceinline__ void await(const Ctx &c, uint32_t &ph) {
+    mbar_wait(c.bar, ph);
+    ph ^= 1u;
+    fence_after();
+}
+
+// D (+)= A(hi,lo) x W(hi,lo): three products per K-chunk; A chunk c = 8 columns of hi pairs then 8 columns of lo pairs
+__device__ __forceinline__ void mma_value(uint32_t d, uint32_t a0, uint64_t desc_hi, uint64_t desc_lo, uint32_t idesc) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint64_t bh = desc_hi + c * B_KSTEP_DESC, bl = desc_lo + c * B_KSTEP_DESC;
+        mma_ts(d, a0 + 16 * c, bh, idesc, c > 0);
+        mma_ts(d, a0 + 16 * c, bl, idesc, 1);
+        mma_ts(d, a0 + 16 * c + 8, bh, idesc, 1);
+    }
+}
+// D (+)= A(hi) x W(hi[,lo]); A chunk c = 8 columns
+__device__ __forceinline__ void mma_tangent(uint32_t d, uint32_t a0, uint64_t desc_hi, uint64_t desc_lo, uint32_t idesc) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        mma_ts(d, a0 + 8 * c, desc_hi + c * B_KSTEP_DESC, idesc, c > 0);
+        if (TANGENT_PRODUCTS == 2) mma_ts(d, a0 + 8 * c, desc_lo + c * B_KSTEP_DESC, idesc, 1);
+    }
+}
+
+template <typename F>
+__device__ __forceinline__ void issue(const Ctx &c, F &&f) {
+    if (c.leader) {
+        fence_after();
+        if (elect_one()) {
+            f();
+            commit(c.bar);
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ float2 as_f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
+
+// One net of one tile.  NET 0 = a (w1: 12x4 matrix, 48 outputs), NET 1 = b (w2: 2x12 matrix, 24 outputs).
+// Net a runs first and leaves per z-row r: tz = tanh(z_r), A_r = g_z dz_r/dtheta, B_r = g_z dz_r/dv in sZ;
+// net b then accumulates this thread's share (rows 6h .. 6h+5) of the head sums into acc[4] = {u0, u1, du0/dtheta, du1/dv}.
+template <int NET>
+__device__ __forceinline__ void chain(const Ctx &c, uint32_t &ph, const float4 in, const float4 xe, float (&acc)[4]) {
+    constexpr int N3 = NET == 0 ? N3A : N3B;
+    const float *sp = c.small + NET * SMALL_NET_FLOATS;
+    const uint64_t w2h = make_bdesc(c.sbase + (NET == 0 ? OFF_W2A_HI : OFF_W2B_HI), B_LBO, B_SBO);
+    const uint64_t w2l = make_bdesc(c.sbase + (NET == 0 ? OFF_W2A_LO : OFF_W2B_LO), B_LBO, B_SBO);
+    const uint64_t w3h = make_bdesc(c.sbase + (NET == 0 ? OFF_W3A_HI : OFF_W3B_HI), B_LBO, B_SBO);
+    const uint64_t w3l = make_bdesc(c.sbase + (NET == 0 ? OFF_W3A_LO : OFF_W3B_LO), B_LBO, B_SBO);
+    constexpr uint32_t idesc128 = make_idesc(128), idesc3 = make_idesc(N3);
+    const int h = c.h;
+
+    // ---- L1: layer 1 on CUDA cores -> value operand in RA; gates g1 = 1 - h1^2 stay in registers ----------------------
+    uint32_t g1[32];
+    {
+        const float4 *W1P = reinterpret_cast<const float4 *>(sp + SP_W1P);
+        const float2 *B1P = reinterpret_cast<const float2 *>(sp + SP_B1P);
+        const float2 ix = make_float2(in.x, in.x), iy = make_float2(in.y, in.y), iz = make_float2(in.z, in.z),
+                     iw = make_float2(in.w, in.w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ch = 4 * h + i;
+            uint32_t av[16];
+#pragma unroll
+            for (int pq = 0; pq < 8; ++pq) {
+                const int pair = 8 * ch + pq;
+                const float4 wa = W1P[2 * pair], wb = W1P[2 * pair + 1];
+                float2 y = __ffma2_rn(make_float2(wa.x, wa.y), ix, B1P[pair]);
+                y = __ffma2_rn(make_float2(wa.z, wa.w), iy, y);
+                y = __ffma2_rn(make_float2(wb.x, wb.y), iz, y);
+                y = __ffma2_rn(make_float2(wb.z, wb.w), iw, y);
+                float2 t, g;
+                tanh_gate2(y, t, g);
+                split_h2(t, av[pq], av[8 + pq]);
+                g1[8 * i + pq] = pack_h2(g.x, g.y);
+            }
+            st16(c.ra + 16 * ch, av);
+        }
+    }
+    publish(c);
+    issue(c, [&] { mma_value(c.RD, c.RA, w2h, w2l, idesc128); });
+    await(c, ph);
+
+    // ---- C1: layer-2 value epilogue, in place; g1 parked in RA[0:64) -----------------------------------------------------
+    uint32_t gs[32];
+    {
+        const float2 *B2P = reinterpret_cast<const float2 *>(sp + SP_B2P);
+        const float2 cs = make_float2(C2SCALE, C2SCALE);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ch = 4 * h + i;
+            uint32_t d[16], av[16];
+            ld16(c.rd + 16 * ch, d);
+            wait_ld();
+#pragma unroll
+            for (int pq = 0; pq < 8; ++pq) {
+                const float2 y = __ffma2_rn(as_f2(d[2 * pq], d[2 * pq + 1]), cs, B2P[8 * ch + pq]);
+                float2 t, g;
+                tanh_gate2(y, t, g);
+                split_h2(t, av[pq], av[8 + pq]);
+                gs[8 * i + pq] = pack_h2(g.x, g.y);
+            }
+            st16(c.rd + 16 * ch, av);
+            st8(c.ra + 8 * ch, &g1[8 * i]);
+        }
+    }
+    publish(c);
+    issue(c, [&] { mma_value(c.RA + 64, c.RD, w3h, w3l, idesc3); });
+    await(c, ph);
+
+    // ---- R4: layer-3 value outputs -------------------------------------------------------------------------------------------
+    const float *b3 = sp + SP_B3;
+    float gz[6];
+    if (NET == 0) {
+        // w1 rows 6h .. 6h+5 (columns 24h .. 24h+23): z_r = w1[r,:] . xe, tz, g_z; A0 = g_z w1[r,2], B0 = g_z w1[r,3]
+        uint32_t v[24];
+        ld8(c.ra + 64 + 24 * h, v);
+        ld8(c.ra + 64 + 24 * h + 8, v + 8);
+        ld8(c.ra + 64 + 24 * h + 16, v + 16);
+        wait_ld();
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr) {
+            const int r = 6 * h + rr;
+            const float4 bb = *reinterpret_cast<const float4 *>(b3 + 4 * r);
+            const float w0 = fmaf(__uint_as_float(v[4 * rr + 0]), INV_WSCALE, bb.x);
+            const float w1 = fmaf(__uint_as_float(v[4 * rr + 1]), INV_WSCALE, bb.y);
+            const float w2 = fmaf(__uint_as_float(v[4 * rr + 2]), INV_WSCALE, bb.z);
+            const float w3 = fmaf(__uint_as_float(v[4 * rr + 3]), INV_WSCALE, bb.w);
+            float z = w0 * xe.x;
+            z = fmaf(w1, xe.y, z);
+            z = fmaf(w2, xe.z, z);
+            z = fmaf(w3, xe.w, z);
+            const float tz = tanh_fast(z);
+            gz[rr] = fmaf(-tz, tz, 1.0f);
+            c.sZ[(0 * 12 + r) * TILE + c.s] = tz;
+            c.sZ[(1 * 12 + r) * TILE + c.s] = gz[rr] * w2;  // + d xe2 / d theta * w1[r][2]
+            c.sZ[(2 * 12 + r) * TILE + c.s] = gz[rr] * w3;  // + d xe3 / d v * w1[r][3]
+        }
+    } else {
+        // w2[0][r], w2[1][r] (columns r, 12 + r) for rows 6h .. 6h+5
+        uint32_t v[24];
+        ld16(c.ra + 64, v);
+        ld8(c.ra + 64 + 16, v + 16);
+        wait_ld();
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr) {
+            const int r = 6 * h + rr;
+            const float d0 = __uint_as_float(h ? v[6 + rr] : v[rr]);
+            const float d1 = __uint_as_float(h ? v[18 + rr] : v[12 + rr]);
+            const float w20 = fmaf(d0, INV_WSCALE, b3[r]), w21 = fmaf(d1, INV_WSCALE, b3[12 + r]);
+            const float tz = c.sZ[(0 * 12 + r) * TILE + c.s];
+            acc[0] = fmaf(w20, tz, acc[0]);
+            acc[1] = fmaf(w21, tz, acc[1]);
+            acc[2] = fmaf(w20, c.sZ[(1 * 12 + r) * TILE + c.s], acc[2]);
+            acc[3] = fmaf(w21, c.sZ[(2 * 12 + r) * TILE + c.s], acc[3]);
+        }
+    }
+    // ---- tangent seeds g1 * W1[:,theta], g1 * W1[:,v] -> RD (the layer-3 value operand is dead) ---------------------------------
+    {
+        const uint32_t *c0h = reinterpret_cast<const uint32_t *>(sp + SP_C0H), *c1h = reinterpret_cast<const uint32_t *>(sp + SP_C1H);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ch = 4 * h + i;
+            uint32_t g[8], at0[8], at1[8];
+            ld8(c.ra + 8 * ch, g);
+            wait_ld();
+#pragma unroll
+            for (int pq = 0; pq < 8; ++pq) {
+                at0[pq] = h2_bits(__hmul2(bits_h2(g[pq]), bits_h2(c0h[8 * ch + pq])));
+                at1[pq] = h2_bits(__hmul2(bits_h2(g[pq]), bits_h2(c1h[8 * ch + pq])));
+            }
+            st8(c.rd + 8 * ch, at0);
+            st8(c.rd + 64 + 8 * ch, at1);
+        }
+    }
+    publish(c);
+    issue(c, [&] { mma_tangent(c.RA, c.RD, w2h, w2l, idesc128); });
+    await(c, ph);
+
+    // ---- C2 / C3: layer-2 tangent epilogues: g2 * accumulator -> RD in place of the seed ---------------------------------------
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ch = 4 * h + i;
+            uint32_t d[16], at[8];
+            ld16(c.ra + 16 * ch, d);
+            wait_ld();
+#pragma unroll
+            for (int pq = 0; pq < 8; ++pq) {
+                const __half2 dh = __floats2half2_rn(__uint_as_float(d[2 * pq]), __uint_as_float(d[2 * pq + 1]));
+                at[pq] = h2_bits(__hmul2(dh, bits_h2(gs[8 * i + pq])));
+            }
+            st8(c.rd + 64 * k + 8 * ch, at);
+        }
+        publish(c);
+        if (k == 0) {
+            issue(c, [&] { mma_tangent(c.RA, c.RD + 64, w2h, w2l, idesc128); });
+        } else {
+            issue(c, [&] {
+                mma_tangent(c.RA, c.RD, w3h, w3l, idesc3);
+                mma_tangent(c.RA + N3, c.RD + 64, w3h, w3l, idesc3);
+            });
+        }
+        await(c, ph);
+    }
+
+    // ---- R56: layer-3 tangent outputs ---------------------------------------------------------------------------------------------
+    if (NET == 0) {
+        uint32_t a[24], b[24];
+        ld8(c.ra + 24 * h, a);
+        ld8(c.ra + 24 * h + 8, a + 8);
+        ld8(c.ra + 24 * h + 16, a + 16);
+        ld8(c.ra + N3 + 24 * h, b);
+        ld8(c.ra + N3 + 24 * h + 8, b + 8);
+        ld8(c.ra + N3 + 24 * h + 16, b + 16);
+        wait_ld();
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr) {
+            const int r = 6 * h + rr;
+            float dzt = __uint_as_float(a[4 * rr + 0]) * xe.x;
+            dzt = fmaf(__uint_as_float(a[4 * rr + 1]), xe.y, dzt);
+            dzt = fmaf(__uint_as_float(a[4 * rr + 2]), xe.z, dzt);
+            dzt = fmaf(__uint_as_float(a[4 * rr + 3]), xe.w, dzt);
+            float dzv = __uint_as_float(b[4 * rr + 0]) * xe.x;
+            dzv = fmaf(__uint_as_float(b[4 * rr + 1]), xe.y, dzv);
+            dzv = fmaf(__uint_as_float(b[4 * rr + 2]), xe.z, dzv);
+            dzv = fmaf(__uint_as_float(b[4 * rr + 3]), xe.w, dzv);
+            const float gi = gz[rr] * INV_S2;
+            c.sZ[(1 * 12 + r) * TILE + c.s] = fmaf(gi, dzt, c.sZ[(1 * 12 + r) * TILE + c.s]);
+            c.sZ[(2 * 12 + r) * TILE + c.s] = fmaf(gi, dzv, c.sZ[(2 * 12 + r) * TILE + c.s]);
+        }
+    } else {
+        // d w2[0][r] / d theta = theta accumulator column r; d w2[1][r] / d v = v accumulator column 12 + r
+        uint32_t a[16], b[16];
+        ld16(c.ra, a);
+        ld16(c.ra + N3 + 8, b);  // v accumulator columns 8 .. 23
+        wait_ld();
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr) {
+            const int r = 6 * h + rr;
+            const float dt0 = __uint_as_float(h ? a[6 + rr] : a[rr]) * INV_S2;
+            const float dv1 = __uint_as_float(h ? b[10 + rr] : b[4 + rr]) * INV_S2;
+            const float tz = c.sZ[(0 * 12 + r) * TILE + c.s];
+            acc[2] = fmaf(dt0, tz, acc[2]);
+            acc[3] = fmaf(dv1, tz, acc[3]);
+        }
+    }
+}
+
+struct SampleState {
+    float x0, x1, x2, x3, x4, rho, margin;
+};
+
+// one Euler step of state and (log-)density from the head sums (get_next_x :124, get_next_rho(log) :136-157)
+__device__ __forceinline__ void sample_advance(const RolloutParams &p, SampleState &st, float u0r, float u1r, float pd0, float pd1) {
+    const float dt = p.dt;
+    st.margin = fminf(st.margin, fminf(fabsf(fabsf(u0r) - 3.0f), fabsf(fabsf(u1r) - 3.0f)));
+    if (p.flags & DP_DENSITY) {
+        const float m0 = (u0r >= -3.0f && u0r <= 3.0f) ? 1.0f : 0.0f;  // inclusive, as the backward of torch.clip
+        const float m1 = (u1r >= -3.0f && u1r <= 3.0f) ? 1.0f : 0.0f;
+        const float div = __fadd_rn(__fmul_rn(m0, pd0), __fmul_rn(m1, pd1));
+        if (p.flags & DP_LOG_DENSITY)
+            st.rho = __fadd_rn(st.rho, logf(__fsub_rn(1.0f, __fmul_rn(div, dt))));
+        else
+            st.rho = __fadd_rn(st.rho, __fmul_rn(__fmul_rn(-div, st.rho), dt));
+    }
+    const float u0 = fminf(fmaxf(u0r, -3.0f), 3.0f), u1 = fminf(fmaxf(u1r, -3.0f), 3.0f);
+    float sn, cs;
+    sincosf(st.x2, &sn, &cs);
+    st.x0 = __fadd_rn(st.x0, __fmul_rn(__fmul_rn(st.x3, cs), dt));
+    st.x1 = __fadd_rn(st.x1, __fmul_rn(__fmul_rn(st.x3, sn), dt));
+    st.x2 = __fadd_rn(st.x2, __fmul_rn(u0, dt));
+    st.x3 = __fadd_rn(st.x3, __fmul_rn(u1, dt));
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) rollout_tcg_kernel(RolloutParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp / GW, wl = warp % GW, q = wl & 3, h = wl >> 2;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+    uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 32);
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(p.tc);
+        int4 *dst = reinterpret_cast<int4 *>(smem);
+        for (int i = tid; i < IMAGE_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(bars), 1);
+        mbar_init(smem_u32(bars + 1), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // make the generic-proxy writes of the weight image visible to the async proxy (tcgen05.mma reads smem through it)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tm = *tmem_ptr_s;
+
+    Ctx c;
+    const uint32_t R0 = tm + 256u * grp, R1 = R0 + 128u, lane_off = (uint32_t)(32 * q) << 16;
+    c.bar = smem_u32(bars + grp);
+    c.sbase = smem_u32(smem);
+    c.bar_id = 1 + grp;
+    c.h = h;
+    c.s = 32 * q + lane;
+    c.leader = wl == 0;
+    c.small = reinterpret_cast<const float *>(smem + OFF_SMALL);
+    c.sZ = reinterpret_cast<float *>(smem + OFF_Z) + grp * 36 * TILE;
+    float *sPart = reinterpret_cast<float *>(smem + OFF_PART) + grp * 2 * 4 * TILE;
+    uint32_t ph = 0;
+
+    const int T = p.T, T1 = p.T + 1;
+    const bool logd = p.flags & DP_LOG_DENSITY, dens = p.flags & DP_DENSITY, cut = p.flags & DP_CUT;
+    const bool abs_state = p.flags & DP_ABS_STATE;
+    const int nd = (p.flags & DP_XY_ONLY) ? 2 : 5;
+    const long long num_tiles = (p.N + TILE - 1) / TILE;
+
+    for (long long tile = (long long)blockIdx.x * NGROUPS + grp; tile < num_tiles; tile += (long long)gridDim.x * NGROUPS) {
+        const long long n = tile * TILE + c.s;
+        const bool valid = n < p.N;
+        const long long nl = valid ? n : p.N - 1;
+        SampleState st;
+        st.x0 = __ldg(p.xe0 + nl * 5 + 0) + __ldg(p.xref + 0 * T1);
+        st.x1 = __ldg(p.xe0 + nl * 5 + 1) + __ldg(p.xref + 1 * T1);
+        st.x2 = __ldg(p.xe0 + nl * 5 + 2) + __ldg(p.xref + 2 * T1);
+        st.x3 = __ldg(p.xe0 + nl * 5 + 3) + __ldg(p.xref + 3 * T1);
+        st.x4 = __ldg(p.xe0 + nl * 5 + 4) + __ldg(p.xref + 4 * T1);
+        st.rho = p.rho0 ? __ldg(p.rho0 + nl) : (logd ? 0.0f : 1.0f);
+        st.margin = 1e30f;
+        int next_store = 0, slot = 0;
+        for (int i = 0;; ++i) {
+            const float xr0 = __ldg(p.xref + 0 * T1 + i), xr1 = __ldg(p.xref + 1 * T1 + i);
+            const float xr2 = __ldg(p.xref + 2 * T1 + i), xr3 = __ldg(p.xref + 3 * T1 + i);
+            if (i == next_store) {
+                // stored slice: the owner thread (h == 0) of each sample writes; a warp covers 32 consecutive samples per row
+                if (h == 0) {
+                    float r = st.rho;
+                    if (cut && dens) {
+                        int fl = 0;
+                        if (r > 1e30f) { r = 1e30f; fl |= 1; }
+                        if (!logd && r < 0.0f) { r = 0.0f; fl |= 1; }
+                        if (r != r) { r = 1e30f; fl |= 2; }
+                        if (fl && valid && p.status) {
+                            if (fl & 1) atomicOr(p.status, 1);
+                            if (fl & 2) atomicOr(p.status + 1, 1);
+                        }
+                    }
+                    if (valid) {
+                        if (p.x_out) {
+                            float *o = p.x_out + (long long)slot * nd * p.ldn + n;
+                            if (abs_state) {
+                                o[0] = st.x0;
+                                o[p.ldn] = st.x1;
+                                if (nd == 5) { o[2 * p.ldn] = st.x2; o[3 * p.ldn] = st.x3; o[4 * p.ldn] = st.x4; }
+                            } else {
+                                o[0] = st.x0 - xr0;
+                                o[p.ldn] = st.x1 - xr1;
+                                if (nd == 5) {
+                                    o[2 * p.ldn] = st.x2 - xr2;
+                                    o[3 * p.ldn] = st.x3 - xr3;
+                                    o[4 * p.ldn] = st.x4 - __ldg(p.xref + 4 * T1 + i);
+                                }
+                            }
+                        }
+                        if (p.rho_out && dens) p.rho_out[(long long)slot * p.ldn + n] = r;
+                    }
+                }
+                next_store += p.stride;
+                ++slot;
+            }
+            if (i == T) break;
+            // Controller.__call__ (sytem_CAR.py:33-34) and the network input of U_FUNC.forward (model_CAR.py:24)
+            const float e0 = st.x0 - xr0, e1 = st.x1 - xr1, e3 = st.x3 - xr3;
+            const float e2 = __fadd_rn(__fsub_rn(st.x2, xr2), st.x4);
+            const float4 in = make_float4(st.x2, st.x3, st.x2 - e2, st.x3 - e3);
+            const float4 xe = make_float4(e0, e1, e2, e3);
+            const float ur0 = __ldg(p.uref + i), ur1 = __ldg(p.uref + T + i);
+
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            {
+                Ctx ca = c;
+                ca.RA = R0; ca.RD = R1; ca.ra = R0 + lane_off; ca.rd = R1 + lane_off;
+                chain<0>(ca, ph, in, xe, acc);
+                ca.RA = R1; ca.RD = R0; ca.ra = R1 + lane_off; ca.rd = R0 + lane_off;
+                chain<1>(ca, ph, in, xe, acc);
+            }
+            // exchange the partial head sums of the two feature halves (fixed order: both threads get identical totals)
+            float *mine = sPart + h * 4 * TILE + c.s;
+            mine[0 * TILE] = acc[0]; mine[1 * TILE] = acc[1]; mine[2 * TILE] = acc[2]; mine[3 * TILE] = acc[3];
+            fence_before();
+            group_sync(c.bar_id);
+            const float *p0 = sPart + c.s, *p1 = sPart + 4 * TILE + c.s;
+            const float pu0 = p0[0 * TILE] + p1[0 * TILE], pu1 = p0[1 * TILE] + p1[1 * TILE];
+            const float pd0 = p0[2 * TILE] + p1[2 * TILE], pd1 = p0[3 * TILE] + p1[3 * TILE];
+            sample_advance(p, st, pu0 + ur0, pu1 + ur1, pd0, pd1);
+        }
+        if (h == 0 && valid && p.clip_margin) p.clip_margin[n] = st.margin;
+    }
+
+    fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
+    }
+}
+
+}  // namespace
+
+// operand image of this kernel: the tensor-core weight images of rollout_tc.cu's layout + this kernel's fp32 block
+int dp_tcg_prepare(dp_controller *c, const float *blob) {
+    std::vector<unsigned char> img(IMAGE_BYTES, 0);
+    const float *p = blob;
+    const int nouts[2] = {DP_NOUT_A, DP_NOUT_B}, nrows3[2] = {N3A, N3B};
+    const int off_w2h[2] = {OFF_W2A_HI, OFF_W2B_HI}, off_w2l[2] = {OFF_W2A_LO, OFF_W2B_LO};
+    const int off_w3h[2] = {OFF_W3A_HI, OFF_W3B_HI}, off_w3l[2] = {OFF_W3A_LO, OFF_W3B_LO};
+    const double k = 2.8853900817779268;  // 2 log2(e)
+    for (int m = 0; m < 2; ++m) {
+        float *sp = reinterpret_cast<float *>(img.data() + OFF_SMALL) + m * SMALL_NET_FLOATS;
+        const float *W1 = p; p += 512;
+        const float *b1 = p; p += 128;
+        for (int j = 0; j < 64; ++j) {
+            for (int cc = 0; cc < 4; ++cc) {
+                sp[SP_W1P + 8 * j + 2 * cc + 0] = (float)(k * W1[4 * (2 * j) + cc]);
+                sp[SP_W1P + 8 * j + 2 * cc + 1] = (float)(k * W1[4 * (2 * j + 1) + cc]);
+            }
+            __half2 c0 = __floats2half2_rn(W1[4 * (2 * j)], W1[4 * (2 * j + 1)]);
+            __half2 c1 = __floats2half2_rn(W1[4 * (2 * j) + 1], W1[4 * (2 * j + 1) + 1]);
+            memcpy(sp + SP_C0H + j, &c0, 4);
+            memcpy(sp + SP_C1H + j, &c1, 4);
+        }
+        for (int j = 0; j < 128; ++j) sp[SP_B1P + j] = (float)(k * b1[j]);
+        build_split_image(p, 128, 128, WSCALE, reinterpret_cast<__half *>(img.data() + off_w2h[m]),
+                          reinterpret_cast<__half *>(img.data() + off_w2l[m]));
+        p += 128 * 128;
+        for (int j = 0; j < 128; ++j) sp[SP_B2P + j] = (float)(k * p[j]);
+        p += 128;
+        build_split_image(p, nouts[m], nrows3[m], WSCALE, reinterpret_cast<__half *>(img.data() + off_w3h[m]),
+                          reinterpret_cast<__half *>(img.data() + off_w3l[m]));
+        p += nouts[m] * 128;
+        memcpy(sp + SP_B3, p, sizeof(float) * nouts[m]);
+        p += nouts[m];
+    }
+    void *d = nullptr;
+    DP_CUDA(cudaMalloc(&d, IMAGE_BYTES));
+    DP_CUDA(cudaMemcpy(d, img.data(), IMAGE_BYTES, cudaMemcpyHostToDevice));
+    c->d_tcg = d;
+    return 0;
+}
+
+void dp_tcg_release(dp_controller *c) {
+    if (c->d_tcg) cudaFree(c->d_tcg);
+    c->d_tcg = nullptr;
+}
+
+int dp_launch_rollout_tcg(const dp_controller *c, const RolloutParams &p, cudaStream_t stream) {
+    DP_REQUIRE(c->d_tcg != nullptr, "DP_IMPL_TCG: tensor-core weight image missing");
+    static bool attr_set[64] = {};
+    if (!attr_set[c->device & 63]) {
+        DP_CUDA(cudaFuncSetAttribute(rollout_tcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        attr_set[c->device & 63] = true;
+    }
+    RolloutParams q = p;
+    q.tc = c->d_tcg;
+    const long long num_tiles = (p.N + TILE - 1) / TILE;
+    const long long want = (num_tiles + NGROUPS - 1) / NGROUPS;
+    const int grid = (int)(want < c->num_sms ? want : c->num_sms);
+    rollout_tcg_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(q);
+    DP_CUDA(cudaGetLastError());
+    return 0;
+}

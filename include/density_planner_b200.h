@@ -43,6 +43,7 @@ extern "C" {
 #define DP_IMPL_DEFAULT 0x000u
 #define DP_IMPL_FFMA 0x100u   /* fp32 CUDA-core kernel                                                         */
 #define DP_IMPL_TC 0x200u     /* tcgen05 tensor-core kernel, split-precision operands (fp32-level accuracy)    */
+#define DP_IMPL_TCG 0x300u    /* tcgen05 kernel, two independent tile pipelines per CTA                        */
 
 /* number of fp32 values in a packed controller blob (see dp_controller_create) */
 #define DP_CONTROLLER_BLOB_FLOATS 43592

@@ -13,7 +13,7 @@ torch.manual_seed(3)
 up, uref, xref = car.get_valid_ref(args)
 uref, xref = uref[:, :, :T], xref[:, :, :T + 1]
 xe0 = car.sample_xe0(N)
-xe, rho, margin = car.compute_density(xe0.cuda(), xref, uref, args.dt_sim, log_density=True, impl="tc", return_margin=True, stride=stride)
+xe, rho, margin = car.compute_density(xe0.cuda(), xref, uref, args.dt_sim, log_density=True, impl=os.environ.get("DP_IMPL", "tc"), return_margin=True, stride=stride)
 torch.cuda.synchronize()
 o_xe, o_rho, o_m, _ = O.rollout(O.load_weights(), xe0[:, :, 0].numpy(), xref[0].numpy(), uref[0].numpy(), args.dt_sim, want_margin=True, stride=stride)
 xe, rho, margin = xe.cpu().numpy(), rho[:, 0, :].cpu().numpy(), margin.cpu().numpy()
