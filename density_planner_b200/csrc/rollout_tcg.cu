@@ -42,10 +42,8 @@ constexpr int GW = 8;             // warps per group
 constexpr int GT = GW * 32;       // threads per group
 constexpr int NGROUPS = 2;
 constexpr int NTHREADS = NGROUPS * GT;
-#ifndef DP_TANGENT_PRODUCTS
-#define DP_TANGENT_PRODUCTS 2     // 2: fp16 tangent activations x (hi + lo) weights; 1: hi weights only
-#endif
-constexpr int TANGENT_PRODUCTS = DP_TANGENT_PRODUCTS;
+// kernel variants (template parameters): TP = tangent products (2: fp16 tangent activations x (hi + lo) weights; 1: hi
+// weights only), TOKEN = hand-off of the MUFU-heavy half of a chain between the two groups (0 off, 1 on)
 
 // per-net fp32 block of the operand image (this kernel's own layout of the "small" section)
 constexpr int SP_W1P = 0;    // [64 pairs][8]: {wx_j, wx_j1, wy_j, wy_j1 | wz_j, wz_j1, ww_j, ww_j1} * 2 log2(e)
@@ -66,7 +64,18 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr float C2SCALE = INV_WSCALE * TWO_LOG2E;        // accumulator (x16) -> 2 log2(e) * pre-activation
 constexpr float INV_S2 = INV_WSCALE * INV_WSCALE;        // layer-3 tangent accumulators carry both x16 factors
 
+// optional in-kernel timeline (DP_TC_TRACE): CTA 0, lane 0 of warps {0, 7, 8, 15}, first TRACE_CHAINS chains
+constexpr int TRACE_CHAINS = 12, TRACE_EVENTS = 16, TRACE_WHO = 4;
+#define TRACE(ev)                                                                                                   \
+    do {                                                                                                            \
+        if (c.trace && c.tchain < TRACE_CHAINS) c.trace[(c.who * TRACE_CHAINS + c.tchain) * TRACE_EVENTS + (ev)] = clock64(); \
+    } while (0)
+
 struct Ctx {
+    unsigned long long *trace;  // null unless this thread records
+    int who, tchain;
+    int grp, nchain;    // group index, chains completed by this group
+
     uint32_t RA, RD;    // lane-0 TMEM addresses of the two regions (MMA operands / accumulators)
     uint32_t ra, rd;    // the same with this warp's lane offset (tcgen05.ld / st)
     uint32_t bar;       // the group's mbarrier
@@ -104,11 +113,49 @@ __device__ __forceinline__ void mma_value(uint32_t d, uint32_t a0, uint64_t desc
     }
 }
 // D (+)= A(hi) x W(hi[,lo]); A chunk c = 8 columns
+template <int TANGENT_PRODUCTS>
 __device__ __forceinline__ void mma_tangent(uint32_t d, uint32_t a0, uint64_t desc_hi, uint64_t desc_lo, uint32_t idesc) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         mma_ts(d, a0 + 8 * c, desc_hi + c * B_KSTEP_DESC, idesc, c > 0);
         if (TANGENT_PRODUCTS == 2) mma_ts(d, a0 + 8 * c, desc_lo + c * B_KSTEP_DESC, idesc, 1);
+    }
+}
+
+// one K-chunk (16 features) of the three-product value MMA
+__device__ __forceinline__ void mma_value_k(uint32_t d, uint32_t a0, uint64_t desc_hi, uint64_t desc_lo, uint32_t idesc, int kc,
+                                            bool first) {
+    const uint64_t bh = desc_hi + kc * B_KSTEP_DESC, bl = desc_lo + kc * B_KSTEP_DESC;
+    mma_ts(d, a0 + 16 * kc, bh, idesc, first ? 0u : 1u);
+    mma_ts(d, a0 + 16 * kc, bl, idesc, 1);
+    mma_ts(d, a0 + 16 * kc + 8, bh, idesc, 1);
+}
+template <int TANGENT_PRODUCTS>
+__device__ __forceinline__ void mma_tangent_k(uint32_t d, uint32_t a0, uint64_t desc_hi, uint64_t desc_lo, uint32_t idesc, int kc,
+                                              bool first) {
+    mma_ts(d, a0 + 8 * kc, desc_hi + kc * B_KSTEP_DESC, idesc, first ? 0u : 1u);
+    if (TANGENT_PRODUCTS == 2) mma_ts(d, a0 + 8 * kc, desc_lo + kc * B_KSTEP_DESC, idesc, 1);
+}
+
+// K-chunked issue: in iteration i of an operand-producing loop every thread has just stored its 16-feature chunk
+// (chunks i and 4 + i of the tile are complete once the whole group got here).  The other warps only ARRIVE on the
+// chunk's named barrier and carry on with the next chunk; the leader warp waits for them and issues the MMAs of those
+// two K-chunks, so the tensor pipe works through the batch while the CUDA cores are still producing the rest of it.
+template <typename F>
+__device__ __forceinline__ void chunk_issue(const Ctx &c, int i, bool last, F &&f) {
+    wait_st();
+    fence_before();
+    const int id = 5 + 4 * c.grp + i;
+    if (c.leader) {
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GT) : "memory");
+        fence_after();
+        if (elect_one()) {
+            f();
+            if (last) commit(c.bar);
+        }
+        __syncwarp();
+    } else {
+        asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(GT) : "memory");
     }
 }
 
@@ -129,8 +176,8 @@ __device__ __forceinline__ float2 as_f2(uint32_t a, uint32_t b) { return make_fl
 // One net of one tile.  NET 0 = a (w1: 12x4 matrix, 48 outputs), NET 1 = b (w2: 2x12 matrix, 24 outputs).
 // Net a runs first and leaves per z-row r: tz = tanh(z_r), A_r = g_z dz_r/dtheta, B_r = g_z dz_r/dv in sZ;
 // net b then accumulates this thread's share (rows 6h .. 6h+5) of the head sums into acc[4] = {u0, u1, du0/dtheta, du1/dv}.
-template <int NET>
-__device__ __forceinline__ void chain(const Ctx &c, uint32_t &ph, const float4 in, const float4 xe, float (&acc)[4]) {
+template <int NET, int TP, int TOKEN, int KC>
+__device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const float4 in, const float4 xe, float (&acc)[4]) {
     constexpr int N3 = NET == 0 ? N3A : N3B;
     const float *sp = c.small + NET * SMALL_NET_FLOATS;
     const uint64_t w2h = make_bdesc(c.sbase + (NET == 0 ? OFF_W2A_HI : OFF_W2B_HI), B_LBO, B_SBO);
@@ -141,6 +188,16 @@ __device__ __forceinline__ void chain(const Ctx &c, uint32_t &ph, const float4 i
     const int h = c.h;
 
     // ---- L1: layer 1 on CUDA cores -> value operand in RA; gates g1 = 1 - h1^2 stay in registers ----------------------
+    // The first half of a chain (L1, C1) is bound by the MUFU pipe, the second half by the tensor pipe: the two groups
+    // pass a token so that one group's first half runs against the other group's second half instead of in lockstep.
+    if (TOKEN) {
+        if (c.grp == 0) {
+            if (c.nchain > 0) asm volatile("bar.sync 4, %0;" ::"n"(NTHREADS) : "memory");
+        } else {
+            asm volatile("bar.sync 3, %0;" ::"n"(NTHREADS) : "memory");
+        }
+    }
+    TRACE(0);
     uint32_t g1[32];
     {
         const float4 *W1P = reinterpret_cast<const float4 *>(sp + SP_W1P);
@@ -152,24 +209,42 @@ __device__ __forceinline__ void chain(const Ctx &c, uint32_t &ph, const float4 i
             const int ch = 4 * h + i;
             uint32_t av[16];
 #pragma unroll
-            for (int pq = 0; pq < 8; ++pq) {
-                const int pair = 8 * ch + pq;
-                const float4 wa = W1P[2 * pair], wb = W1P[2 * pair + 1];
-                float2 y = __ffma2_rn(make_float2(wa.x, wa.y), ix, B1P[pair]);
-                y = __ffma2_rn(make_float2(wa.z, wa.w), iy, y);
-                y = __ffma2_rn(make_float2(wb.x, wb.y), iz, y);
-                y = __ffma2_rn(make_float2(wb.z, wb.w), iw, y);
-                float2 t, g;
-                tanh_gate2(y, t, g);
-                split_h2(t, av[pq], av[8 + pq]);
-                g1[8 * i + pq] = pack_h2(g.x, g.y);
+            for (int pq = 0; pq < 8; pq += 2) {
+                float2 y[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int pair = 8 * ch + pq + e;
+                    const float4 wa = W1P[2 * pair], wb = W1P[2 * pair + 1];
+                    y[e] = __ffma2_rn(make_float2(wa.x, wa.y), ix, B1P[pair]);
+                    y[e] = __ffma2_rn(make_float2(wa.z, wa.w), iy, y[e]);
+                    y[e] = __ffma2_rn(make_float2(wb.x, wb.y), iz, y[e]);
+                    y[e] = __ffma2_rn(make_float2(wb.z, wb.w), iw, y[e]);
+                }
+                float2 t[2], g[2];
+                tanh_gate4(y[0], y[1], t[0], t[1], g[0], g[1]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    split_h2(t[e], av[pq + e], av[8 + pq + e]);
+                    g1[8 * i + pq + e] = pack_h2(g[e].x, g[e].y);
+                }
             }
             st16(c.ra + 16 * ch, av);
+            if (KC)
+                chunk_issue(c, i, i == 3, [&] {
+                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, i, i == 0);
+                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 4 + i, false);
+                });
         }
     }
-    publish(c);
-    issue(c, [&] { mma_value(c.RD, c.RA, w2h, w2l, idesc128); });
+    TRACE(1);
+    if (!KC) {
+        publish(c);
+        TRACE(2);
+        issue(c, [&] { mma_value(c.RD, c.RA, w2h, w2l, idesc128); });
+    }
+    TRACE(3);
     await(c, ph);
+    TRACE(4);
 
     // ---- C1: layer-2 value epilogue, in place; g1 parked in RA[0:64) -----------------------------------------------------
     uint32_t gs[32];
@@ -183,24 +258,47 @@ __device__ __forceinline__ void chain(const Ctx &c, uint32_t &ph, const float4 i
             ld16(c.rd + 16 * ch, d);
             wait_ld();
 #pragma unroll
-            for (int pq = 0; pq < 8; ++pq) {
-                const float2 y = __ffma2_rn(as_f2(d[2 * pq], d[2 * pq + 1]), cs, B2P[8 * ch + pq]);
-                float2 t, g;
-                tanh_gate2(y, t, g);
-                split_h2(t, av[pq], av[8 + pq]);
-                gs[8 * i + pq] = pack_h2(g.x, g.y);
+            for (int pq = 0; pq < 8; pq += 2) {
+                const float2 y0 = __ffma2_rn(as_f2(d[2 * pq], d[2 * pq + 1]), cs, B2P[8 * ch + pq]);
+                const float2 y1 = __ffma2_rn(as_f2(d[2 * pq + 2], d[2 * pq + 3]), cs, B2P[8 * ch + pq + 1]);
+                float2 t[2], g[2];
+                tanh_gate4(y0, y1, t[0], t[1], g[0], g[1]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    split_h2(t[e], av[pq + e], av[8 + pq + e]);
+                    gs[8 * i + pq + e] = pack_h2(g[e].x, g[e].y);
+                }
             }
             st16(c.rd + 16 * ch, av);
             st8(c.ra + 8 * ch, &g1[8 * i]);
+            if (KC)
+                chunk_issue(c, i, i == 3, [&] {
+                    mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, i, i == 0);
+                    mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, 4 + i, false);
+                });
         }
     }
-    publish(c);
-    issue(c, [&] { mma_value(c.RA + 64, c.RD, w3h, w3l, idesc3); });
+    TRACE(5);
+    if (TOKEN) {
+        if (c.grp == 0)
+            asm volatile("bar.arrive 3, %0;" ::"n"(NTHREADS) : "memory");
+        else
+            asm volatile("bar.arrive 4, %0;" ::"n"(NTHREADS) : "memory");
+    }
+    if (!KC) {
+        publish(c);
+        issue(c, [&] { mma_value(c.RA + 64, c.RD, w3h, w3l, idesc3); });
+    }
+    TRACE(6);
     await(c, ph);
+    TRACE(7);
 
     // ---- R4: layer-3 value outputs -------------------------------------------------------------------------------------------
     const float *b3 = sp + SP_B3;
     float gz[6];
+    uint32_t gst[32];  // the parked layer-1 gates, fetched together with the layer-3 outputs (one TMEM round trip)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld8(c.ra + 8 * (4 * h + i), gst + 8 * i);
     if (NET == 0) {
         // w1 rows 6h .. 6h+5 (columns 24h .. 24h+23): z_r = w1[r,:] . xe, tz, g_z; A0 = g_z w1[r,2], B0 = g_z w1[r,3]
         uint32_t v[24];
@@ -251,48 +349,59 @@ __device__ __forceinline__ void chain(const Ctx &c, uint32_t &ph, const float4 i
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int ch = 4 * h + i;
-            uint32_t g[8], at0[8], at1[8];
-            ld8(c.ra + 8 * ch, g);
-            wait_ld();
+            uint32_t at0[8], at1[8];
 #pragma unroll
             for (int pq = 0; pq < 8; ++pq) {
-                at0[pq] = h2_bits(__hmul2(bits_h2(g[pq]), bits_h2(c0h[8 * ch + pq])));
-                at1[pq] = h2_bits(__hmul2(bits_h2(g[pq]), bits_h2(c1h[8 * ch + pq])));
+                at0[pq] = h2_bits(__hmul2(bits_h2(gst[8 * i + pq]), bits_h2(c0h[8 * ch + pq])));
+                at1[pq] = h2_bits(__hmul2(bits_h2(gst[8 * i + pq]), bits_h2(c1h[8 * ch + pq])));
             }
             st8(c.rd + 8 * ch, at0);
             st8(c.rd + 64 + 8 * ch, at1);
+            if (KC)  // every thread reaches its first arrival after all its reads of RA (outputs, parked gates) completed
+                chunk_issue(c, i, i == 3, [&] {
+                    mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, i, i == 0);
+                    mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, 4 + i, false);
+                });
         }
     }
-    publish(c);
-    issue(c, [&] { mma_tangent(c.RA, c.RD, w2h, w2l, idesc128); });
+    TRACE(8);
+    if (!KC) {
+        publish(c);
+        issue(c, [&] { mma_tangent<TP>(c.RA, c.RD, w2h, w2l, idesc128); });
+    }
+    TRACE(9);
     await(c, ph);
+    TRACE(10);
 
     // ---- C2 / C3: layer-2 tangent epilogues: g2 * accumulator -> RD in place of the seed ---------------------------------------
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 4; i += 2) {
             const int ch = 4 * h + i;
-            uint32_t d[16], at[8];
+            uint32_t d[32], at[16];
             ld16(c.ra + 16 * ch, d);
+            ld16(c.ra + 16 * ch + 16, d + 16);
             wait_ld();
 #pragma unroll
-            for (int pq = 0; pq < 8; ++pq) {
+            for (int pq = 0; pq < 16; ++pq) {
                 const __half2 dh = __floats2half2_rn(__uint_as_float(d[2 * pq]), __uint_as_float(d[2 * pq + 1]));
                 at[pq] = h2_bits(__hmul2(dh, bits_h2(gs[8 * i + pq])));
             }
-            st8(c.rd + 64 * k + 8 * ch, at);
+            st16(c.rd + 64 * k + 8 * ch, at);
         }
+        TRACE(11 + 2 * k);
         publish(c);
         if (k == 0) {
-            issue(c, [&] { mma_tangent(c.RA, c.RD + 64, w2h, w2l, idesc128); });
+            issue(c, [&] { mma_tangent<TP>(c.RA, c.RD + 64, w2h, w2l, idesc128); });
         } else {
             issue(c, [&] {
-                mma_tangent(c.RA, c.RD, w3h, w3l, idesc3);
-                mma_tangent(c.RA + N3, c.RD + 64, w3h, w3l, idesc3);
+                mma_tangent<TP>(c.RA, c.RD, w3h, w3l, idesc3);
+                mma_tangent<TP>(c.RA + N3, c.RD + 64, w3h, w3l, idesc3);
             });
         }
         await(c, ph);
+        TRACE(12 + 2 * k);
     }
 
     // ---- R56: layer-3 tangent outputs ---------------------------------------------------------------------------------------------
@@ -336,6 +445,9 @@ __device__ __forceinline__ void chain(const Ctx &c, uint32_t &ph, const float4 i
             acc[3] = fmaf(dv1, tz, acc[3]);
         }
     }
+    TRACE(15);
+    ++c.tchain;
+    ++c.nchain;
 }
 
 struct SampleState {
@@ -364,6 +476,7 @@ __device__ __forceinline__ void sample_advance(const RolloutParams &p, SampleSta
     st.x3 = __fadd_rn(st.x3, __fmul_rn(u1, dt));
 }
 
+template <int TP, int TOKEN, int KC>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_tcg_kernel(RolloutParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -402,6 +515,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tcg_kernel(RolloutParams 
     c.leader = wl == 0;
     c.small = reinterpret_cast<const float *>(smem + OFF_SMALL);
     c.sZ = reinterpret_cast<float *>(smem + OFF_Z) + grp * 36 * TILE;
+    c.who = (warp == 0) ? 0 : (warp == 7) ? 1 : (warp == 8) ? 2 : (warp == 15) ? 3 : -1;
+    c.trace = (p.trace && blockIdx.x == 0 && lane == 0 && c.who >= 0) ? p.trace : nullptr;
+    c.tchain = 0;
+    c.grp = grp;
+    c.nchain = 0;
     float *sPart = reinterpret_cast<float *>(smem + OFF_PART) + grp * 2 * 4 * TILE;
     uint32_t ph = 0;
 
@@ -411,7 +529,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tcg_kernel(RolloutParams 
     const int nd = (p.flags & DP_XY_ONLY) ? 2 : 5;
     const long long num_tiles = (p.N + TILE - 1) / TILE;
 
-    for (long long tile = (long long)blockIdx.x * NGROUPS + grp; tile < num_tiles; tile += (long long)gridDim.x * NGROUPS) {
+    // both groups run the same number of chains (a group without a tile in the last round runs a dummy one: the token
+    // hand-off is symmetric)
+    const long long num_rounds = (num_tiles + NGROUPS - 1) / NGROUPS;
+    for (long long round = blockIdx.x; round < num_rounds; round += gridDim.x) {
+        const long long tile = round * NGROUPS + grp;
         const long long n = tile * TILE + c.s;
         const bool valid = n < p.N;
         const long long nl = valid ? n : p.N - 1;
@@ -473,13 +595,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tcg_kernel(RolloutParams 
             const float ur0 = __ldg(p.uref + i), ur1 = __ldg(p.uref + T + i);
 
             float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            {
-                Ctx ca = c;
-                ca.RA = R0; ca.RD = R1; ca.ra = R0 + lane_off; ca.rd = R1 + lane_off;
-                chain<0>(ca, ph, in, xe, acc);
-                ca.RA = R1; ca.RD = R0; ca.ra = R1 + lane_off; ca.rd = R0 + lane_off;
-                chain<1>(ca, ph, in, xe, acc);
-            }
+            c.RA = R0; c.RD = R1; c.ra = R0 + lane_off; c.rd = R1 + lane_off;
+            chain<0, TP, TOKEN, KC>(c, ph, in, xe, acc);
+            c.RA = R1; c.RD = R0; c.ra = R1 + lane_off; c.rd = R0 + lane_off;
+            chain<1, TP, TOKEN, KC>(c, ph, in, xe, acc);
             // exchange the partial head sums of the two feature halves (fixed order: both threads get identical totals)
             float *mine = sPart + h * 4 * TILE + c.s;
             mine[0 * TILE] = acc[0]; mine[1 * TILE] = acc[1]; mine[2 * TILE] = acc[2]; mine[3 * TILE] = acc[3];
@@ -493,6 +612,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tcg_kernel(RolloutParams 
         if (h == 0 && valid && p.clip_margin) p.clip_margin[n] = st.margin;
     }
 
+    if (TOKEN && grp == 0 && c.nchain > 0) asm volatile("bar.sync 4, %0;" ::"n"(NTHREADS) : "memory");  // the last hand-off
     fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -552,16 +672,49 @@ void dp_tcg_release(dp_controller *c) {
 int dp_launch_rollout_tcg(const dp_controller *c, const RolloutParams &p, cudaStream_t stream) {
     DP_REQUIRE(c->d_tcg != nullptr, "DP_IMPL_TCG: tensor-core weight image missing");
     static bool attr_set[64] = {};
+    static int variant = -1;  // tuning / A-B knob: DP_TCG_VARIANT = 100 * k_chunked + 10 * tangent_products + token
+    typedef void (*kern_t)(RolloutParams);
+    static const kern_t kerns[8] = {rollout_tcg_kernel<1, 0, 0>, rollout_tcg_kernel<1, 1, 0>, rollout_tcg_kernel<2, 0, 0>,
+                                    rollout_tcg_kernel<2, 1, 0>, rollout_tcg_kernel<1, 0, 1>, rollout_tcg_kernel<1, 1, 1>,
+                                    rollout_tcg_kernel<2, 0, 1>, rollout_tcg_kernel<2, 1, 1>};
+    if (variant < 0) {
+        const char *e = getenv("DP_TCG_VARIANT");
+        const int v = e ? atoi(e) : 110;
+        variant = ((v / 100) ? 4 : 0) + (((v / 10) % 10 == 1) ? 0 : 2) + ((v % 10) ? 1 : 0);
+    }
     if (!attr_set[c->device & 63]) {
-        DP_CUDA(cudaFuncSetAttribute(rollout_tcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        for (int k = 0; k < 8; ++k)
+            DP_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_set[c->device & 63] = true;
     }
+    const kern_t kern = kerns[variant];
     RolloutParams q = p;
     q.tc = c->d_tcg;
     const long long num_tiles = (p.N + TILE - 1) / TILE;
     const long long want = (num_tiles + NGROUPS - 1) / NGROUPS;
     const int grid = (int)(want < c->num_sms ? want : c->num_sms);
-    rollout_tcg_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(q);
+    const char *trace_path = getenv("DP_TC_TRACE");  // diagnostic: dump an in-kernel clock64 timeline of CTA 0
+    if (trace_path) {
+        const size_t n = (size_t)TRACE_WHO * TRACE_CHAINS * TRACE_EVENTS;
+        DP_CUDA(cudaMalloc(&q.trace, n * 8));
+        DP_CUDA(cudaMemsetAsync(q.trace, 0, n * 8, stream));
+        kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(q);
+        DP_CUDA(cudaStreamSynchronize(stream));
+        std::vector<unsigned long long> hbuf(n);
+        DP_CUDA(cudaMemcpy(hbuf.data(), q.trace, n * 8, cudaMemcpyDeviceToHost));
+        cudaFree(q.trace);
+        if (FILE *f = fopen(trace_path, "w")) {
+            for (int w = 0; w < TRACE_WHO; ++w)
+                for (int sl = 0; sl < TRACE_CHAINS; ++sl) {
+                    fprintf(f, "%d %d", w, sl);
+                    for (int e = 0; e < TRACE_EVENTS; ++e) fprintf(f, " %llu", hbuf[((size_t)w * TRACE_CHAINS + sl) * TRACE_EVENTS + e]);
+                    fprintf(f, "\n");
+                }
+            fclose(f);
+        }
+        return 0;
+    }
+    kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(q);
     DP_CUDA(cudaGetLastError());
     return 0;
 }

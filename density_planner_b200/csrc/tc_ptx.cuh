@@ -150,6 +150,28 @@ __device__ __forceinline__ void tanh_gate2(const float2 y, float2 &t, float2 &g)
     t = __ffma2_rn(make_float2(-2.0f, -2.0f), r, one);
     g = __ffma2_rn(make_float2(-t.x, -t.y), t, one);
 }
+// four tanh at once with ONE reciprocal: e = 2^-|y| in (0, 1] so a = 1 + e in (1, 2] and the product of four a's cannot
+// overflow; 1/a_i is recovered from R = 1 / (a0 a1 a2 a3) with products (three MUFU.RCP traded for a few FMULs: the
+// MUFU pipe, 4 lanes/clk per SM sub-partition, is what bounds the epilogues).  tanh|x| = 2/(1+e) - 1, sign copied from y.
+__device__ __forceinline__ float ex2_negabs(float y) { return ex2_approx(-fabsf(y)); }
+__device__ __forceinline__ float2 copysign2(const float2 mag, const float2 sgn) {  // mag >= 0
+    return make_float2(__uint_as_float(__float_as_uint(mag.x) | (__float_as_uint(sgn.x) & 0x80000000u)),
+                       __uint_as_float(__float_as_uint(mag.y) | (__float_as_uint(sgn.y) & 0x80000000u)));
+}
+__device__ __forceinline__ void tanh_gate4(const float2 yA, const float2 yB, float2 &tA, float2 &tB, float2 &gA, float2 &gB) {
+    const float2 one = make_float2(1.0f, 1.0f), two = make_float2(2.0f, 2.0f), mone = make_float2(-1.0f, -1.0f);
+    const float2 aA = __fadd2_rn(make_float2(ex2_negabs(yA.x), ex2_negabs(yA.y)), one);
+    const float2 aB = __fadd2_rn(make_float2(ex2_negabs(yB.x), ex2_negabs(yB.y)), one);
+    const float2 p = __fmul2_rn(aA, aB);                       // (a0 a2, a1 a3)
+    const float R = rcp_approx(p.x * p.y);
+    const float2 q = make_float2(R * p.y, R * p.x);            // (1/(a0 a2), 1/(a1 a3))
+    const float2 rA = __fmul2_rn(q, aB), rB = __fmul2_rn(q, aA);  // (1/a0, 1/a1), (1/a2, 1/a3)
+    const float2 mA = __ffma2_rn(two, rA, mone), mB = __ffma2_rn(two, rB, mone);  // tanh|x|
+    gA = __ffma2_rn(make_float2(-mA.x, -mA.y), mA, one);
+    gB = __ffma2_rn(make_float2(-mB.x, -mB.y), mB, one);
+    tA = copysign2(mA, yA);
+    tB = copysign2(mB, yB);
+}
 __device__ __forceinline__ uint32_t h2_bits(const __half2 h) { return *reinterpret_cast<const uint32_t *>(&h); }
 __device__ __forceinline__ __half2 bits_h2(const uint32_t u) { return *reinterpret_cast<const __half2 *>(&u); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) { return h2_bits(__floats2half2_rn(a, b)); }  // a -> low half
