@@ -12,7 +12,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 # flags (include/density_planner_b200.h)
 DP_LOG_DENSITY, DP_DENSITY, DP_CUT, DP_ABS_STATE, DP_XY_ONLY = 1, 2, 4, 8, 16
-DP_IMPL_DEFAULT, DP_IMPL_FFMA, DP_IMPL_TC, DP_IMPL_TCG = 0x000, 0x100, 0x200, 0x300
+DP_IMPL_DEFAULT, DP_IMPL_FFMA, DP_IMPL_TC = 0x000, 0x100, 0x200
 DP_CONTROLLER_BLOB_FLOATS = 43592
 
 

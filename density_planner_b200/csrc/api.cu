@@ -64,7 +64,7 @@ int dp_controller_create(const float *blob, size_t n_floats, int device, dp_cont
     DP_CUDA(cudaMemcpy(c->d_big, big.data(), sizeof(float) * DP_BIG_FLOATS, cudaMemcpyHostToDevice));
     DP_CUDA(cudaMemcpy(c->d_small, small.data(), sizeof(float) * DP_SMALL_FLOATS, cudaMemcpyHostToDevice));
     DP_CUDA(cudaStreamCreateWithFlags(&c->host_stream, cudaStreamNonBlocking));
-    if (dp_tc_prepare(c, blob) != 0 || dp_tcg_prepare(c, blob) != 0) {
+    if (dp_tc_prepare(c, blob) != 0) {
         dp_controller_destroy(c);
         return 3;
     }
@@ -76,7 +76,6 @@ void dp_controller_destroy(dp_controller *c) {
     if (!c) return;
     DeviceGuard guard(c->device);
     dp_tc_release(c);
-    dp_tcg_release(c);
     cudaFree(c->d_big);
     cudaFree(c->d_small);
     cudaFree(c->ws.ptr);
@@ -108,7 +107,6 @@ int dp_rollout(const dp_controller *c, const float *xe0, const float *xref, cons
     // default = the tcgen05 kernel (fp32-level value path); DP_IMPL_FFMA selects the all-fp32 CUDA-core kernel
     if (impl == DP_IMPL_TC || impl == DP_IMPL_DEFAULT) return dp_launch_rollout_tc(c, p, (cudaStream_t)stream);
     if (impl == DP_IMPL_FFMA) return dp_launch_rollout_ffma(c, p, (cudaStream_t)stream);
-    if (impl == DP_IMPL_TCG) return dp_launch_rollout_tcg(c, p, (cudaStream_t)stream);
     dp_set_error("dp_rollout: unknown implementation selector 0x%x", impl);
     return 2;
 }

@@ -40,7 +40,6 @@ struct dp_controller {
     // tensor-core operand images (built by rollout_tc.cu at create time; may be null)
     void *d_tc = nullptr;
     size_t tc_bytes = 0;
-    void *d_tcg = nullptr;  // image of the two-pipeline kernel (rollout_tcg.cu)
     // grow-only device workspace + stream for the *_host entry points
     dp_workspace ws;
     cudaStream_t host_stream = nullptr;
@@ -112,9 +111,6 @@ int dp_launch_rollout_ffma(const dp_controller *c, const RolloutParams &p, cudaS
 int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStream_t stream);
 int dp_tc_prepare(dp_controller *c, const float *host_blob);  // builds c->d_tc
 void dp_tc_release(dp_controller *c);
-int dp_launch_rollout_tcg(const dp_controller *c, const RolloutParams &p, cudaStream_t stream);
-int dp_tcg_prepare(dp_controller *c, const float *host_blob);  // builds c->d_tcg
-void dp_tcg_release(dp_controller *c);
 
 // ---- small device helpers ----------------------------------------------------------------------------------
 // pos2gridpos for one coordinate, fp32 op for op as torch evaluates motion_planning/utils.py:82-85

@@ -196,7 +196,7 @@ class ControlAffineSystem:
                                            % (xref_traj.shape[2], T))
         flags = (_lib.DP_LOG_DENSITY if log_density else 0) | (_lib.DP_DENSITY if compute_density else 0) | \
                 (_lib.DP_CUT if cutting else 0)
-        flags |= {None: _lib.DP_IMPL_DEFAULT, "ffma": _lib.DP_IMPL_FFMA, "tc": _lib.DP_IMPL_TC, "tcg": _lib.DP_IMPL_TCG}[impl]
+        flags |= {None: _lib.DP_IMPL_DEFAULT, "ffma": _lib.DP_IMPL_FFMA, "tc": _lib.DP_IMPL_TC}[impl]
         Ts = T // stride + 1
         status = None
         if N == 0:

@@ -43,7 +43,6 @@ extern "C" {
 #define DP_IMPL_DEFAULT 0x000u
 #define DP_IMPL_FFMA 0x100u   /* fp32 CUDA-core kernel                                                         */
 #define DP_IMPL_TC 0x200u     /* tcgen05 tensor-core kernel, split-precision operands (fp32-level accuracy)    */
-#define DP_IMPL_TCG 0x300u    /* tcgen05 kernel, two independent tile pipelines per CTA                        */
 
 /* number of fp32 values in a packed controller blob (see dp_controller_create) */
 #define DP_CONTROLLER_BLOB_FLOATS 43592
@@ -173,7 +172,7 @@ int dp_normalize_apply(const float *rholog, const float *rho0, int64_t N, int Ts
 
 /* Diagnostic: one 128 x n x 128 product through the TMEM-operand tcgen05.mma path of the tensor-core rollout
  * (split-precision fp16 operands).  A host fp32 [128][128], W host fp32 [n_valid][128] zero-padded to n rows
- * (n in {128, 48, 32}), mode 0 = value path (3 products), 1 = tangent path (2 products); D host fp32 [128][n]
+ * (n in {128, 48, 32}), mode 0 = value path (3 products), 1 = fp16 activations x (hi + lo) weights (2 products); D host fp32 [128][n]
  * receives A * (scale * W)^T. */
 int dp_tc_selftest(int device, const float *A, const float *W, int n_valid, int n, int mode, float scale, float *D);
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""One tcgen05 rollout case vs the oracle: python scripts/tc_case.py N T [stride]  (env DP_TC_MODE selects the kernel)."""
+"""One tcgen05 rollout case vs the oracle: python scripts/tc_case.py N T [stride]  (env DP_IMPL selects the kernel, DP_TC_VARIANT its variant)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -18,5 +18,5 @@ torch.cuda.synchronize()
 o_xe, o_rho, o_m, _ = O.rollout(O.load_weights(), xe0[:, :, 0].numpy(), xref[0].numpy(), uref[0].numpy(), args.dt_sim, want_margin=True, stride=stride)
 xe, rho, margin = xe.cpu().numpy(), rho[:, 0, :].cpu().numpy(), margin.cpu().numpy()
 safe = np.minimum(margin, o_m) > 2e-5
-print("mode=%s N=%d T=%d stride=%d: states %.2e | logdens safe %.2e rel %.2e | unsafe %d" % (os.environ.get("DP_TC_MODE", "0"), N, T, stride,
+print("mode=%s N=%d T=%d stride=%d: states %.2e | logdens safe %.2e rel %.2e | unsafe %d" % (os.environ.get("DP_TC_VARIANT", "-"), N, T, stride,
       np.abs(xe - o_xe).max(), np.abs(rho - o_rho)[safe].max(), (np.abs(rho - o_rho)[safe] / (np.abs(o_rho[safe]) + .1)).max(), int((~safe).sum())))

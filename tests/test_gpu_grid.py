@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden, COST_RTOL
+from conftest import golden, COST_RTOL, RHO_RTOL, RHO_ATOL
 
 pytestmark = pytest.mark.gpu
 
@@ -195,7 +195,15 @@ def test_normalizer_and_planner_le_call(dp, car, oracle, blob, args):
     ref = e["le_rho"]
     got = rho_traj[:, 0, :].numpy()
     big = ref > 1e-6
-    assert np.abs(got[big] / ref[big] - 1).max() < 5e-3
+    # the normalised density is exp(l - max l) rho0 / sum: a relative error of rho is an ABSOLUTE error of the
+    # log-density l, whose contract is rtol 1e-3 (+1e-4) on |l|; |l| reaches ~40 over these 1000 steps.  The oracle
+    # (pinned to the reference at 8e-7 rel) supplies l; factor 2 for the shift of the normaliser itself.
+    uref_long, _ = car.sample_uref_traj(args, up=up)
+    xref_long = car.compute_xref_traj(xref0, uref_long, args)
+    o_rho = oracle.rollout(blob, e["le_xe0"], xref_long[0].numpy(), uref_long[0].numpy(), args.dt_sim, cutting=False)[1]
+    tol = 2 * (RHO_RTOL * np.abs(o_rho).max(axis=0) + RHO_ATOL)   # per time index
+    err = np.abs(np.log(got.clip(1e-30)) - np.log(ref.clip(1e-30)))
+    assert (err <= tol[None, :])[big].all(), "normalised density: max log error %.3g (tol %.3g)" % (err[big].max(), tol.max())
     assert np.abs(got.sum(axis=0) - 1).max() < 1e-4
     # and the cost the planner computes from it
     gx, gy = oracle.env_gradient(e["grid"])

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden, assert_states_close, assert_rho_close, FLIP_MARGIN
+from conftest import golden, assert_states_close, assert_rho_close, FLIP_MARGIN, RHO_RTOL, RHO_ATOL
 
 pytestmark = pytest.mark.gpu
 
@@ -85,7 +85,12 @@ def test_rollout_modes(car, impl):
     rho0 = torch.from_numpy(g["rho0"]).reshape(-1, 1, 1).cuda()
     xe, rho, _ = _run(car, g, impl, stride=s, rho0=rho0, cutting=True, log_density=False)
     assert_states_close(xe, g["xe_lin"], xref_s, "linear")
-    assert np.allclose(rho, g["rho_lin"], rtol=1e-3, atol=1e-6)
+    # linear density rho = rho0 exp(l): a relative error of rho is an absolute error of the log-density l, whose contract is
+    # rtol 1e-3 (+1e-4) on |l| (here |l| reaches 70 within 150 steps)
+    l_ref = np.log(g["rho_lin"] / g["rho0"][:, None])
+    rel = np.abs(rho / g["rho_lin"] - 1)
+    tol = RHO_RTOL * np.abs(l_ref) + RHO_ATOL
+    assert (rel <= tol).all(), "linear density: worst rel err / tol = %.3g" % (rel / tol).max()
     xe, rho, _ = _run(car, g, impl, stride=s, cutting=False, log_density=True)
     assert_rho_close(rho, g["rholog"], None, "log, no cutting")
     xe, rho, _ = _run(car, g, impl, stride=s, compute_density=False)
