@@ -7,8 +7,8 @@
 One "step" = one pass of the hot path over one batch of synthetic input on every rank:
     fused rollout of SAMPLES x STEPS closed-loop sample-steps with Liouville log-density (BASELINE config 2:
     1M samples x 100 steps), slices stored every 10th step  ->  density normaliser  ->  collision cost on the stored
-    slices  ->  occupancy binning of the slices (int64/int32 grids)  [-> NCCL allreduce of normaliser stats, cost and
-    grids when N > 1].
+    slices  ->  occupancy binning of the slices (int64/int32 grids) fused with the obstacle-grid dot product
+    [-> NCCL allreduce of normaliser stats, cost, dot product and grids when N > 1].
 `value` = closed-loop sample-steps/s over all ranks with inputs resident in HBM (CUDA events, max over ranks).
 `e2e`   = the same metric through the public API `Car.compute_density` with HOST tensors (H2D + kernel + D2H of the
           full trajectory inside the timed region).
@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -237,6 +237,7 @@ def main():
     lmax = torch.empty(Ts, dtype=torch.float32, device=dev)
     lsum = torch.empty(Ts, dtype=torch.float64, device=dev)
     cost_slices = torch.empty(Ts, dtype=torch.float64, device=dev)
+    occ_dot = torch.empty(Ts, dtype=torch.float64, device=dev)
     spec = _lib.BinSpec()
     spec.mode = 0
     spec.geom = G._geom(args)
@@ -268,12 +269,14 @@ def main():
                                   _lib.ptr(cost_slices), None, None, None, None, 0, 0, None, sp), "dp_cost_coll")
         mass.zero_()
         count.zero_()
-        _lib.check(L.dp_bin2d(ctypes.byref(spec), _lib.ptr(xs), _lib.ptr(ys), 1, 5 * N, _lib.ptr(rho), 1, N, N, Ts,
-                              _lib.ptr(mass), _lib.ptr(count), sp), "dp_bin2d")
+        _lib.check(L.dp_bin2d_occ(ctypes.byref(spec), denv.handle, _lib.ptr(xs), _lib.ptr(ys), 1, 5 * N, _lib.ptr(rho), 1, N,
+                                  N, Ts, _lib.ptr(mass), _lib.ptr(count), _lib.ptr(occ_dot), sp), "dp_bin2d_occ")
         D.allreduce_sum(cost_slices)
+        D.allreduce_sum(occ_dot)
         D.allreduce_grids(mass, count)
-        # rollout, normalize_stats, normalize_apply, cost (+finalize), 2 memsets, bin2d  (+ NCCL kernels when N > 1)
-        launches["n"] += 8
+        # rollout, normaliser (max, sum, finalize, apply), cost (+finalize), 2 memsets, binning fused with the occupancy dot
+        # product (+finalize)  (+ NCCL kernels when N > 1)
+        launches["n"] += 11
 
     def barrier():
         if world > 1:
@@ -386,7 +389,8 @@ def main():
                        "parallelism": "samples sharded, %d rank(s); allreduce of normaliser stats, cost and int grids" % world},
             "e2e": e2e, "gpu_launches": launches["n"], "clocks": clk, "roofline": roofline,
             "collision_cost_evals_per_s": cost_evals * world,
-            "checks": {"grid_count_total": total_count, "grid_mass_total": total_mass, "cost_total": cost_total}}
+            "checks": {"grid_count_total": total_count, "grid_mass_total": total_mass, "cost_total": cost_total,
+                       "occupancy_dot_total": float(occ_dot.sum().item())}}
     if not opts.no_cpu_baseline and world == 1:
         base, _, _ = cpu_oracle_rate()
         line["cpu_baseline"] = base

@@ -7,7 +7,7 @@ Monte-Carlo rollout of sampled initial states through the CAR closed loop under 
 from ._lib import DensityPlannerError, build, lib  # noqa: F401
 from .hyperparams import default_args  # noqa: F401
 from .systems import Car, ControlAffineSystem, Controller  # noqa: F401
-from .grid import (pos2gridpos, gridpos2pos, pred2grid, check_collision, get_density_map, normalize_density,  # noqa: F401
+from .grid import (pos2gridpos, gridpos2pos, pred2grid, check_collision, get_density_map, normalize_density, bin_occupancy,  # noqa: F401
                    DeviceEnv, get_cost_coll, get_cost_coll_initialize)
 from .planner import EgoPredictor, CollisionCost, attach  # noqa: F401
 from .rawdata import compute_data  # noqa: F401

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "dp_cost_coll": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _i64,
                             _i64, _vp, _vp]),
     "dp_bin2d": (_int, [ctypes.POINTER(BinSpec), _vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp]),
+    "dp_bin2d_occ": (_int, [ctypes.POINTER(BinSpec), _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "dp_normalize_stats": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
     "dp_normalize_apply": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp]),
     "dp_probe_ffma_peak": (_int, [_int, ctypes.POINTER(ctypes.c_double)]),

@@ -1,17 +1,28 @@
 // K3: deterministic grid binning with integer fixed-point accumulation, and the density normaliser.
 //   pred2grid            motion_planning/utils.py:255-280   (mode 0: occupancy-grid cells, clamp to [0, G])
 //   get_density_map      systems/utils.py:105-129           (mode 1: np.histogramdd bins)
+//   check_collision      motion_planning/utils.py:231-252   (occupancy dot product, fused: see occ_dot)
 //   normaliser           motion_planning/simulation_objects.py:295-299
-// Samples of a warp that fall into the same cell are aggregated with match/redux before ONE 64-bit and ONE 32-bit
-// atomic per distinct cell reach L2; integer sums make the result independent of execution order and of how the
-// samples are sharded over GPUs (the per-GPU grids are summed with an integer allreduce).
+// The samples of a slice cluster around the reference trajectory, so every block keeps a WIN x WIN window of cells (int64
+// fixed-point mass + int32 count) in shared memory, centred on a probe of its own samples; samples are accumulated with
+// shared-memory atomics and the window is flushed to the global grids once at the end (one atomic per touched cell per
+// block).  Samples outside the window fall back to warp-aggregated global atomics (match.any + redux).  Integer sums make
+// the result independent of execution order and of how the samples are sharded over GPUs (the per-GPU grids are summed
+// with an integer allreduce).  Optionally the same pass gathers the environment's occupancy of every sample's cell and
+// returns, per slice, sum_s w_s * p[cell_s] = sum_cells mass[cell] * p[cell]: the obstacle-grid dot product of the binned
+// density, without a second pass over the grid.
 #include "dp_common.cuh"
 
 namespace {
 
+constexpr int WIN = 80;                  // window edge in cells
+constexpr int BIN_THREADS = 1024;
+constexpr int BIN_SMEM = WIN * WIN * 12 + 64;
+constexpr int MAX_BIN_PARTIALS = 1 << 15;
+
 struct BinArgs {
     int mode;
-    float x_lo, x_rng, y_lo, y_rng, gxm1, gym1;  // mode 0
+    DpGeom q;                                    // mode 0
     int cx, cy;                                  // cells per axis of the output arrays
     double lo_x, hi_x, lo_y, hi_y;               // mode 1
     double scale;
@@ -20,6 +31,10 @@ struct BinArgs {
     int Ts;
     long long *mass;
     int *count;
+    const float4 *table;  // environment table [t][gx][gy] {p, gX, gY, 0} or null
+    int egx, egy;         // its cells per axis
+    double *partial;      // [Ts][B] partial occupancy dot products or null
+    int B;
 };
 
 // np.histogramdd bin index for `v` over `bins` uniform bins on [lo, hi] (right edge inclusive); -1 if outside.
@@ -37,75 +52,170 @@ __device__ __forceinline__ int hist_bin(double v, double lo, double hi, int bins
     return k;
 }
 
-__global__ void __launch_bounds__(256) bin2d_kernel(BinArgs a) {
-    const int t = blockIdx.y;
+__device__ __forceinline__ void sample_cell(const BinArgs &a, float x, float y, int &ix, int &iy) {
+    if (a.mode == 0) {
+        ix = min(max(dp_cell(x, a.q.x_lo, a.q.x_rng, a.q.r_x_rng, a.q.gxm1), 0), a.cx - 1);  // clamp to [0, G] (:261-262), cx = G+1
+        iy = min(max(dp_cell(y, a.q.y_lo, a.q.y_rng, a.q.r_y_rng, a.q.gym1), 0), a.cy - 1);
+    } else {
+        ix = hist_bin((double)x, a.lo_x, a.hi_x, a.cx);
+        iy = hist_bin((double)y, a.lo_y, a.hi_y, a.cy);
+    }
+}
+
+__global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
+    extern __shared__ __align__(16) unsigned char bsm[];
+    unsigned long long *smass = reinterpret_cast<unsigned long long *>(bsm);
+    int *scount = reinterpret_cast<int *>(bsm + WIN * WIN * 8);
+    int *sorg = reinterpret_cast<int *>(bsm + WIN * WIN * 12);
+    __shared__ double shd[BIN_THREADS / 32];
+    const int t = blockIdx.y, tid = threadIdx.x;
     const float *xp = a.x + (long long)t * a.sx_t;
     const float *yp = a.y + (long long)t * a.sx_t;
     const float *wp = a.w ? a.w + (long long)t * a.sw_t : nullptr;
     const long long cells = (long long)a.cx * a.cy;
     long long *mass = a.mass ? a.mass + (long long)t * cells : nullptr;
     int *count = a.count ? a.count + (long long)t * cells : nullptr;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long nmax = ((a.N + 31) / 32) * 32;  // keep warps converged for the match/redux collectives
-    for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < nmax; n += stride) {
-        int cell = -1;
+    const float4 *tab = a.table ? a.table + (size_t)t * a.egx * a.egy : nullptr;
+    // this block's samples: a contiguous chunk of the slice
+    const long long chunk = (a.N + gridDim.x - 1) / gridDim.x;
+    const long long n_lo = (long long)blockIdx.x * chunk, n_hi = min(n_lo + chunk, a.N);
+    // window origin: mean cell of 32 probe samples spread over the chunk (any choice gives the same integer grids)
+    if (tid < 32) {
+        int ix = 0, iy = 0, ok = 0;
+        if (n_lo < n_hi) {
+            const long long n = n_lo + (n_hi - n_lo) * tid / 32;
+            sample_cell(a, __ldg(xp + n * a.sx_n), __ldg(yp + n * a.sx_n), ix, iy);
+            ok = (ix >= 0 && iy >= 0) ? 1 : 0;
+        }
+        int sx = ok ? ix : 0, sy = ok ? iy : 0, sk = ok;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, m);
+            sy += __shfl_xor_sync(0xffffffffu, sy, m);
+            sk += __shfl_xor_sync(0xffffffffu, sk, m);
+        }
+        if (tid == 0) {
+            const int mx_ = sk ? sx / sk : 0, my_ = sk ? sy / sk : 0;
+            sorg[0] = min(max(mx_ - WIN / 2, 0), max(a.cx - WIN, 0));
+            sorg[1] = min(max(my_ - WIN / 2, 0), max(a.cy - WIN, 0));
+        }
+    }
+    for (int i = tid; i < WIN * WIN; i += BIN_THREADS) {
+        smass[i] = 0ull;
+        scount[i] = 0;
+    }
+    __syncthreads();
+    const int ox = sorg[0], oy = sorg[1];
+    double dot = 0.0;
+    const long long span = n_hi - n_lo;
+    const long long nmax = ((span + 31) / 32) * 32;  // keep warps converged for the match/redux collectives
+    for (long long k = tid; k < nmax; k += BIN_THREADS) {
+        const long long n = n_lo + k;
+        int cell = -1, wcell = -1;
         long long q = 0;
-        if (n < a.N) {
+        if (k < span) {
             const float x = __ldg(xp + n * a.sx_n), y = __ldg(yp + n * a.sx_n);
             int ix, iy;
-            if (a.mode == 0) {
-                ix = min(max(dp_cell(x, a.x_lo, a.x_rng, a.gxm1), 0), a.cx - 1);  // clamp to [0, G] (:261-262), cx = G+1
-                iy = min(max(dp_cell(y, a.y_lo, a.y_rng, a.gym1), 0), a.cy - 1);
-            } else {
-                ix = hist_bin((double)x, a.lo_x, a.hi_x, a.cx);
-                iy = hist_bin((double)y, a.lo_y, a.hi_y, a.cy);
-            }
+            sample_cell(a, x, y, ix, iy);
             if (ix >= 0 && iy >= 0) {
-                cell = ix * a.cy + iy;
                 const double w = wp ? (double)__ldg(wp + n * a.sw_n) : 1.0;
                 q = __double2ll_rn(w * a.scale);
+                const int wx = ix - ox, wy = iy - oy;
+                if (wx >= 0 && wx < WIN && wy >= 0 && wy < WIN)
+                    wcell = wx * WIN + wy;
+                else
+                    cell = ix * a.cy + iy;
+                if (tab && ix < a.egx && iy < a.egy) dot += (double)q * (double)__ldg(&tab[(size_t)ix * a.egy + iy].x);
             }
         }
-        // warp aggregation: lanes with the same cell elect a leader that issues the atomics for the group
-        const unsigned grp = __match_any_sync(0xffffffffu, cell);
-        const int leader = __ffs(grp) - 1;
-        const unsigned lo = (unsigned)(q & 0xFFFFFF), mid = (unsigned)((q >> 24) & 0xFFFFFF);
-        const int hi = (int)(q >> 48);
-        const unsigned slo = __reduce_add_sync(grp, lo), smid = __reduce_add_sync(grp, mid);
-        const int shi = __reduce_add_sync(grp, hi);
-        if (cell >= 0 && (int)(threadIdx.x & 31) == leader) {
-            const long long sum = (long long)slo + ((long long)smid << 24) + ((long long)shi << 48);
-            if (mass) atomicAdd(reinterpret_cast<unsigned long long *>(mass + cell), (unsigned long long)sum);
-            if (count) atomicAdd(count + cell, __popc(grp));
+        if (wcell >= 0) {
+            if (mass) atomicAdd(smass + wcell, (unsigned long long)q);
+            if (count) atomicAdd(scount + wcell, 1);
+        }
+        // samples outside the window: lanes with the same cell elect a leader that issues the global atomics for the group
+        if (__any_sync(0xffffffffu, cell >= 0)) {
+            const unsigned grp = __match_any_sync(0xffffffffu, cell);
+            const int leader = __ffs(grp) - 1;
+            const unsigned lo = (unsigned)(q & 0xFFFFFF), mid = (unsigned)((q >> 24) & 0xFFFFFF);
+            const int hi = (int)(q >> 48);
+            const unsigned slo = __reduce_add_sync(grp, lo), smid = __reduce_add_sync(grp, mid);
+            const int shi = __reduce_add_sync(grp, hi);
+            if (cell >= 0 && (int)(tid & 31) == leader) {
+                const long long sum = (long long)slo + ((long long)smid << 24) + ((long long)shi << 48);
+                if (mass) atomicAdd(reinterpret_cast<unsigned long long *>(mass + cell), (unsigned long long)sum);
+                if (count) atomicAdd(count + cell, __popc(grp));
+            }
+        }
+    }
+    __syncthreads();
+    // flush the window: one atomic per touched cell
+    for (int i = tid; i < WIN * WIN; i += BIN_THREADS) {
+        const int wx = i / WIN, wy = i - wx * WIN;
+        const int ix = ox + wx, iy = oy + wy;
+        if (ix < a.cx && iy < a.cy) {
+            const long long g = (long long)ix * a.cy + iy;
+            const unsigned long long m = smass[i];
+            const int c = scount[i];
+            if (mass && m) atomicAdd(reinterpret_cast<unsigned long long *>(mass + g), m);
+            if (count && c) atomicAdd(count + g, c);
+        }
+    }
+    if (a.partial) {  // fixed-order block reduction of the occupancy dot product
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, m);
+        if ((tid & 31) == 0) shd[tid >> 5] = dot;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < BIN_THREADS / 32; ++w) tot += shd[w];
+            a.partial[(size_t)t * a.B + blockIdx.x] = tot;
         }
     }
 }
 
+__global__ void bin_dot_finalize_kernel(const double *partial, int B, int Ts, double inv_scale, double *occ_dot) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < Ts; t += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int b = 0; b < B; ++b) s += partial[(size_t)t * B + b];
+        occ_dot[t] = s * inv_scale;
+    }
+}
+
 // ---- normaliser ----------------------------------------------------------------------------------------------------
-// one block per time slot: max, then sum of exp(l - max) * rho0 in fp64 with a fixed reduction order
-__global__ void __launch_bounds__(1024) normalize_stats_kernel(const float *__restrict__ rholog,
-                                                               const float *__restrict__ rho0, long long N, long long ldn,
-                                                               float *lmax, double *lsum) {
-    __shared__ float shf[32];
-    __shared__ double shd[32];
-    __shared__ float s_max;
-    const int t = blockIdx.x;
+// per time slot: max, then sum of exp(l - max) * rho0 in fp64; grid (B, Ts) partials, fixed reduction order
+constexpr int NB = 256;  // threads per block
+__global__ void __launch_bounds__(NB) normalize_max_kernel(const float *__restrict__ rholog, long long N, long long ldn,
+                                                           float *pmax, int B) {
+    __shared__ float shf[NB / 32];
+    const int t = blockIdx.y;
     const float *l = rholog + (long long)t * ldn;
     float m = -INFINITY;
-    for (long long n = threadIdx.x; n < N; n += blockDim.x) m = fmaxf(m, __ldg(l + n));
+    for (long long n = (long long)blockIdx.x * NB + threadIdx.x; n < N; n += (long long)gridDim.x * NB) m = fmaxf(m, __ldg(l + n));
 #pragma unroll
     for (int k = 16; k > 0; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
     if ((threadIdx.x & 31) == 0) shf[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
         float mm = -INFINITY;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mm = fmaxf(mm, shf[i]);
+        for (int i = 0; i < NB / 32; ++i) mm = fmaxf(mm, shf[i]);
+        pmax[(size_t)t * B + blockIdx.x] = mm;
+    }
+}
+__global__ void __launch_bounds__(NB) normalize_sum_kernel(const float *__restrict__ rholog, const float *__restrict__ rho0,
+                                                           long long N, long long ldn, const float *pmax, double *psum, int B) {
+    __shared__ double shd[NB / 32];
+    __shared__ float s_max;
+    const int t = blockIdx.y;
+    if (threadIdx.x == 0) {
+        float mm = -INFINITY;
+        for (int b = 0; b < B; ++b) mm = fmaxf(mm, pmax[(size_t)t * B + b]);
         s_max = mm;
     }
     __syncthreads();
     const float mx = s_max;
+    const float *l = rholog + (long long)t * ldn;
     double s = 0.0;
-    for (long long n = threadIdx.x; n < N; n += blockDim.x) {
+    for (long long n = (long long)blockIdx.x * NB + threadIdx.x; n < N; n += (long long)gridDim.x * NB) {
         const float r0 = rho0 ? __ldg(rho0 + n) : 1.0f;
         s += (double)__fmul_rn(expf(__fsub_rn(__ldg(l + n), mx)), r0);
     }
@@ -115,9 +225,20 @@ __global__ void __launch_bounds__(1024) normalize_stats_kernel(const float *__re
     __syncthreads();
     if (threadIdx.x == 0) {
         double tot = 0.0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += shd[i];
-        lmax[t] = mx;
-        lsum[t] = tot;
+        for (int i = 0; i < NB / 32; ++i) tot += shd[i];
+        psum[(size_t)t * B + blockIdx.x] = tot;
+    }
+}
+__global__ void normalize_finalize_kernel(const float *pmax, const double *psum, int B, int Ts, float *lmax, double *lsum) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < Ts; t += gridDim.x * blockDim.x) {
+        float mm = -INFINITY;
+        double s = 0.0;
+        for (int b = 0; b < B; ++b) {
+            mm = fmaxf(mm, pmax[(size_t)t * B + b]);
+            s += psum[(size_t)t * B + b];
+        }
+        lmax[t] = mm;
+        lsum[t] = s;
     }
 }
 
@@ -137,45 +258,97 @@ __global__ void normalize_apply_kernel(const float *__restrict__ rholog, const f
 
 }  // namespace
 
-int dp_bin2d(const dp_bin_spec *spec, const float *x, const float *y, int64_t sx_n, int64_t sx_t, const float *w,
-             int64_t sw_n, int64_t sw_t, int64_t N, int Ts, long long *mass, int *count, void *stream) {
-    DP_REQUIRE(spec && x && y && (mass || count), "dp_bin2d: null argument");
+static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float *x, const float *y, int64_t sx_n, int64_t sx_t,
+                        const float *w, int64_t sw_n, int64_t sw_t, int64_t N, int Ts, long long *mass, int *count,
+                        double *occ_dot, cudaStream_t stream) {
+    DP_REQUIRE(spec && x && y && (mass || count || occ_dot), "dp_bin2d: null argument");
     DP_REQUIRE(spec->mode == 0 || spec->mode == 1, "dp_bin2d: mode must be 0 or 1");
     DP_REQUIRE(spec->mass_scale_log2 >= 0 && spec->mass_scale_log2 <= 62, "dp_bin2d: bad mass_scale_log2");
-    if (N <= 0 || Ts <= 0) return 0;
+    DP_REQUIRE(!occ_dot || (env && spec->mode == 0), "dp_bin2d_occ: the occupancy dot product needs an environment and mode 0");
+    DP_REQUIRE(!occ_dot || Ts <= env->Tg, "dp_bin2d_occ: Ts=%d exceeds the %d time slices of the environment", Ts, occ_dot ? env->Tg : 0);
+    if (Ts <= 0) return 0;
+    if (N <= 0) {
+        if (occ_dot) DP_CUDA(cudaMemsetAsync(occ_dot, 0, sizeof(double) * Ts, stream));
+        return 0;
+    }
     BinArgs a;
+    memset(&a, 0, sizeof(a));
     a.mode = spec->mode;
     if (a.mode == 0) {
-        a.x_lo = spec->geom.x_min; a.x_rng = spec->geom.x_max - spec->geom.x_min;
-        a.y_lo = spec->geom.y_min; a.y_rng = spec->geom.y_max - spec->geom.y_min;
-        a.gxm1 = (float)(spec->geom.gx - 1); a.gym1 = (float)(spec->geom.gy - 1);
+        a.q = dp_make_geom(spec->geom);
         a.cx = spec->geom.gx + 1; a.cy = spec->geom.gy + 1;
-        a.lo_x = a.hi_x = a.lo_y = a.hi_y = 0;
     } else {
         DP_REQUIRE(spec->bx > 0 && spec->by > 0 && spec->hi_x > spec->lo_x && spec->hi_y > spec->lo_y, "dp_bin2d: bad bins");
         a.cx = spec->bx; a.cy = spec->by;
         a.lo_x = spec->lo_x; a.hi_x = spec->hi_x; a.lo_y = spec->lo_y; a.hi_y = spec->hi_y;
-        a.x_lo = a.x_rng = a.y_lo = a.y_rng = a.gxm1 = a.gym1 = 0;
     }
     a.scale = ldexp(1.0, spec->mass_scale_log2);
     a.x = x; a.y = y; a.w = w;
     a.sx_n = sx_n; a.sx_t = sx_t; a.sw_n = sw_n; a.sw_t = sw_t; a.N = N; a.Ts = Ts;
     a.mass = mass; a.count = count;
-    long long B = (N + 255) / 256;
-    const long long target = (148LL * 8 + Ts - 1) / Ts;
+    // ~2 resident blocks of 1024 threads per SM, every block amortises one window flush over >= 8 samples per thread
+    long long B = (N + BIN_THREADS * 8 - 1) / (BIN_THREADS * 8);
+    const long long target = (148LL * 4 + Ts - 1) / Ts;
     if (B > target) B = target;
+    if (B * Ts > MAX_BIN_PARTIALS) B = MAX_BIN_PARTIALS / Ts;
     if (B < 1) B = 1;
-    bin2d_kernel<<<dim3((unsigned)B, (unsigned)Ts), 256, 0, (cudaStream_t)stream>>>(a);
+    a.B = (int)B;
+    double *partial = nullptr;
+    if (occ_dot) {
+        DP_REQUIRE(Ts <= MAX_BIN_PARTIALS, "dp_bin2d_occ: too many slices");
+        DP_CUDA(cudaMallocAsync(&partial, sizeof(double) * B * Ts, stream));
+        a.table = env->d_table;
+        a.egx = env->geom.gx;
+        a.egy = env->geom.gy;
+        a.partial = partial;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        attr_set = true;
+    }
+    bin2d_kernel<<<dim3((unsigned)B, (unsigned)Ts), BIN_THREADS, BIN_SMEM, stream>>>(a);
     DP_CUDA(cudaGetLastError());
+    if (occ_dot) {
+        bin_dot_finalize_kernel<<<(Ts + 127) / 128, 128, 0, stream>>>(partial, a.B, Ts, 1.0 / a.scale, occ_dot);
+        DP_CUDA(cudaGetLastError());
+        DP_CUDA(cudaFreeAsync(partial, stream));
+    }
     return 0;
 }
 
+int dp_bin2d(const dp_bin_spec *spec, const float *x, const float *y, int64_t sx_n, int64_t sx_t, const float *w,
+             int64_t sw_n, int64_t sw_t, int64_t N, int Ts, long long *mass, int *count, void *stream) {
+    DP_REQUIRE(mass || count, "dp_bin2d: null argument");
+    return bin2d_launch(spec, nullptr, x, y, sx_n, sx_t, w, sw_n, sw_t, N, Ts, mass, count, nullptr, (cudaStream_t)stream);
+}
+
+int dp_bin2d_occ(const dp_bin_spec *spec, const dp_env *env, const float *x, const float *y, int64_t sx_n, int64_t sx_t,
+                 const float *w, int64_t sw_n, int64_t sw_t, int64_t N, int Ts, long long *mass, int *count, double *occ_dot,
+                 void *stream) {
+    DP_REQUIRE(env && occ_dot, "dp_bin2d_occ: null argument");
+    DeviceGuard guard(env->device);
+    return bin2d_launch(spec, env, x, y, sx_n, sx_t, w, sw_n, sw_t, N, Ts, mass, count, occ_dot, (cudaStream_t)stream);
+}
+
 int dp_normalize_stats(const float *rholog, const float *rho0, int64_t N, int Ts, int64_t ldn, float *lmax,
-                       double *lsum_at_max, void *stream) {
+                       double *lsum_at_max, void *stream_) {
     DP_REQUIRE(rholog && lmax && lsum_at_max, "dp_normalize_stats: null argument");
     if (N <= 0 || Ts <= 0) return 0;
-    normalize_stats_kernel<<<Ts, 1024, 0, (cudaStream_t)stream>>>(rholog, rho0, N, ldn, lmax, lsum_at_max);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    long long B = (N + NB * 8 - 1) / (NB * 8);
+    const long long target = (148LL * 16 + Ts - 1) / Ts;
+    if (B > target) B = target;
+    if (B < 1) B = 1;
+    float *pmax = nullptr;
+    double *psum = nullptr;
+    DP_CUDA(cudaMallocAsync(&psum, (sizeof(double) + sizeof(float)) * B * Ts, stream));
+    pmax = reinterpret_cast<float *>(psum + B * Ts);
+    normalize_max_kernel<<<dim3((unsigned)B, (unsigned)Ts), NB, 0, stream>>>(rholog, N, ldn, pmax, (int)B);
+    normalize_sum_kernel<<<dim3((unsigned)B, (unsigned)Ts), NB, 0, stream>>>(rholog, rho0, N, ldn, pmax, psum, (int)B);
+    normalize_finalize_kernel<<<(Ts + 127) / 128, 128, 0, stream>>>(pmax, psum, (int)B, Ts, lmax, lsum_at_max);
     DP_CUDA(cudaGetLastError());
+    DP_CUDA(cudaFreeAsync(psum, stream));
     return 0;
 }
 

@@ -104,6 +104,31 @@ def bin2d_raw(spec, x, y, w, N, Ts, sx, sw, device):
     return mass, count
 
 
+def bin_occupancy(denv, x, y, w, args, mass_scale=None):
+    """Time-sliced occupancy binning fused with the obstacle-grid dot product (dp_bin2d_occ).
+
+    x, y, w: CUDA float32 tensors [Ts][N] (this library's time-major layout; w = normalised density per slice).
+    Returns (mass int64 [Ts][G0+1][G1+1], count int32 [Ts][G0+1][G1+1], occ_dot float64 [Ts], scale_log2) where
+    occ_dot[t] = sum_s w[t,s] * grid[cell(s), t] = sum_cells mass[t] * grid[:, :, t] / 2**scale_log2, the collision
+    probability mass `check_collision` (motion_planning/utils.py:231-252) thresholds for a sum-binned density."""
+    L = _lib.lib()
+    Ts, N = x.shape
+    dev = x.device
+    spec = _lib.BinSpec()
+    spec.mode = 0
+    spec.geom = _geom(args)
+    spec.mass_scale_log2 = mass_scale if mass_scale is not None else mass_scale_log2(N, float(w.abs().max()) if N > 0 else 1.0)
+    cx, cy = spec.geom.gx + 1, spec.geom.gy + 1
+    mass = torch.zeros((Ts, cx, cy), dtype=torch.int64, device=dev)
+    count = torch.zeros((Ts, cx, cy), dtype=torch.int32, device=dev)
+    dot = torch.empty(Ts, dtype=torch.float64, device=dev)
+    assert x.is_contiguous() and y.is_contiguous() and w.is_contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(L.dp_bin2d_occ(ctypes.byref(spec), denv.handle, _lib.ptr(x), _lib.ptr(y), 1, N, _lib.ptr(w), 1, N, N, Ts,
+                                  _lib.ptr(mass), _lib.ptr(count), _lib.ptr(dot), _lib.current_stream(dev)), "dp_bin2d_occ")
+    return mass, count, dot, spec.mass_scale_log2
+
+
 def pred2grid(x, rho, args, return_gridpos=False):
     """Mean density per occupied cell, normalised to 1 (motion_planning/utils.py:255-280).
 

@@ -143,7 +143,7 @@ int dp_cost_coll(const dp_env *e, const float *x, const float *y, int64_t sx_n, 
  * mode 1: uniform bins like np.histogramdd (systems/utils.py:105-129): bins (bx, by) over [lo, hi], right edge
  *         inclusive, samples outside dropped; grid arrays are bx x by per slice.
  *   w      dev weights (same addressing as x with sw_n, sw_t) or NULL (weight 1)
- *   mass   dev int64 [Ts][cells]: sum of llrint(w * 2^mass_scale_log2)  (accumulated with atomics: exact, order-free)
+ *   mass   dev int64 [Ts][cells]: sum of llrint(w * 2^mass_scale_log2)  (shared-memory window + atomics: exact, order-free)
  *   count  dev int32 [Ts][cells]
  *   occ, occ_cost: if occ != NULL (dev float [cells][To] reference-layout occupancy grid is NOT used here; see
  *          dp_cost_coll) -- reserved, pass NULL.
@@ -158,6 +158,17 @@ typedef struct dp_bin_spec {
 
 int dp_bin2d(const dp_bin_spec *spec, const float *x, const float *y, int64_t sx_n, int64_t sx_t, const float *w,
              int64_t sw_n, int64_t sw_t, int64_t N, int Ts, long long *mass, int *count, void *stream);
+
+/*
+ * dp_bin2d (mode 0) plus, in the same pass over the samples, the obstacle-grid dot product of the binned density:
+ *   occ_dot dev double[Ts]:  sum_s w_s * p[t][cell_s]  =  sum_cells mass[t][cell] * p[t][cell] / 2^mass_scale_log2,
+ * i.e. the quantity check_collision (motion_planning/utils.py:231-252) thresholds, for the sum-binned density.  Samples on
+ * the clamp cell G (outside the environment grid) contribute nothing.  mass / count may be NULL.  Per-slice sums are
+ * reduced in a fixed order (deterministic).
+ */
+int dp_bin2d_occ(const dp_bin_spec *spec, const dp_env *env, const float *x, const float *y, int64_t sx_n, int64_t sx_t,
+                 const float *w, int64_t sw_n, int64_t sw_t, int64_t N, int Ts, long long *mass, int *count,
+                 double *occ_dot, void *stream);
 
 /*
  * Density normaliser of EgoVehicle.predict_density (motion_planning/simulation_objects.py:295-299), per time slot:

@@ -93,6 +93,36 @@ def test_binning_counts_exact_and_order_free(dp, oracle, args):
     assert np.abs(got - ref).max() < 1e-6
 
 
+def test_binning_fused_occupancy_dot(dp, args):
+    """dp_bin2d_occ: time-sliced binning (shared-memory window + global fall-back) equals the slice-by-slice binning, and
+    the fused obstacle-grid dot product equals sum_cells mass * grid computed from the grids afterwards."""
+    from density_planner_b200 import _lib, grid as G
+    e, denv, _, _ = _env(dp, args, 2)
+    Ts, N = 7, 200_003
+    g = torch.Generator(device="cuda").manual_seed(5)
+    tt = torch.linspace(0, 1, Ts, device="cuda")
+    # slice-dependent spread: tight clouds (all in the window), wide clouds (fall-back path) and samples beyond the grid
+    sig = torch.tensor([0.3, 0.6, 1.5, 4.0, 9.0, 0.1, 20.0], device="cuda")[:, None]
+    x = (0.5 * torch.sin(3 * tt))[:, None] + sig * torch.randn(Ts, N, device="cuda", generator=g)
+    y = (-28 + 36 * tt)[:, None] + sig * torch.randn(Ts, N, device="cuda", generator=g)
+    w = torch.rand(Ts, N, device="cuda", generator=g)
+    w = (w / w.sum(dim=1, keepdim=True)).contiguous()
+    mass, cnt, dot, sc = dp.bin_occupancy(denv, x.contiguous(), y.contiguous(), w, args)
+    assert int(cnt.sum()) == Ts * N
+    spec = _lib.BinSpec()
+    spec.mode = 0
+    spec.geom = G._geom(args)
+    spec.mass_scale_log2 = sc
+    dev = x.device
+    for t in range(Ts):
+        m1, c1 = G.bin2d_raw(spec, x[t].contiguous(), y[t].contiguous(), w[t].contiguous(), N, 1, (1, 0), (1, 0), dev)
+        assert bool((m1[0] == mass[t]).all()) and bool((c1[0] == cnt[t]).all())
+    grid = torch.from_numpy(e["grid"]).cuda().double()  # (241, 401, 101)
+    ref = (mass[:, :241, :401].double() * grid[:, :, :Ts].permute(2, 0, 1)).sum(dim=(1, 2)) / 2.0 ** sc
+    assert float(((dot - ref).abs() / ref.abs().clamp(min=1e-30)).max()) < 1e-10
+    assert float(ref.max()) > 0
+
+
 def _env(dp, args, seed):
     e = golden("env_seed%d.npz" % seed)
     import dp_oracle
