@@ -308,7 +308,8 @@ def main():
     cost_total = float(cost_slices.sum().item())
 
     # ---- end to end through the public API with host tensors ---------------------------------------------------------
-    xe0_cpu = xe0_host  # (N,5,1) pinned
+    Ne = min(N, SAMPLES)  # the full (N,5,T+1)+(N,1,T+1) trajectory comes back to the host: cap it at the config-2 size
+    xe0_cpu = xe0_host[:Ne]  # (Ne,5,1) pinned
     impl = opts.kernel
     # warm the host path at full size (pinned result buffers come from torch's caching host allocator afterwards)
     _w = car.compute_density(xe0_cpu, xref, uref, args.dt_sim, log_density=True, cutting=True, impl=impl)
@@ -325,8 +326,8 @@ def main():
         t_sum += time.perf_counter() - t0
     t_e2e = D.max_over_ranks(t_sum / e2e_steps, dev)
     # context for the e2e number: the raw pinned device->host copy rate of this box for the same byte count
-    probe_dev = torch.empty((T + 1) * 6 * N, dtype=torch.float32, device=dev)
-    probe_host = torch.empty((T + 1) * 6 * N, dtype=torch.float32, pin_memory=True)
+    probe_dev = torch.empty((T + 1) * 6 * Ne, dtype=torch.float32, device=dev)
+    probe_host = torch.empty((T + 1) * 6 * Ne, dtype=torch.float32, pin_memory=True)
     probe_host.copy_(probe_dev)
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
@@ -334,9 +335,9 @@ def main():
     torch.cuda.synchronize(dev)
     d2h_gbs = probe_dev.numel() * 4 / (time.perf_counter() - t0) / 1e9
     del probe_dev, probe_host
-    e2e = {"value": world * N * T / t_e2e, "unit": UNIT,
-           "h2d_bytes_per_step": int(4 * (N * 5 + 5 * (T + 1) + 2 * T)),
-           "d2h_bytes_per_step": int(4 * (T + 1) * 6 * N),
+    e2e = {"value": world * Ne * T / t_e2e, "unit": UNIT, "samples_per_gpu": Ne,
+           "h2d_bytes_per_step": int(4 * (Ne * 5 + 5 * (T + 1) + 2 * T)),
+           "d2h_bytes_per_step": int(4 * (T + 1) * 6 * Ne),
            "api": "Car.compute_density(xe0, xref_traj, uref_traj, dt, log_density=True) with CPU tensors "
                   "(dp_rollout_host: H2D + kernel + D2H of the full (N,5,T+1)+(N,1,T+1) trajectory)",
            "ms_per_step": 1e3 * t_e2e, "pinned_d2h_gbs_measured": d2h_gbs}
@@ -355,6 +356,53 @@ def main():
     torch.cuda.synchronize(dev)
     cost_ms = c0.elapsed_time(c1) / reps
     cost_evals = N * Ts / (cost_ms * 1e-3)
+
+    # ---- BASELINE config 3: collision cost (forward, forward+backward) and fused binning on 1M weighted samples x 101
+    #      time slices of the environment, [t][n] layout, inputs resident in HBM (1.2 GB streamed per pass > L2) -------
+    cfg3 = None
+    if rank == 0:
+        del x_out, l_out, rho, mass, count
+        N3, T3 = SAMPLES, 101
+        g3 = torch.Generator(device=dev).manual_seed(1)
+        tt = torch.linspace(0, 1, T3, device=dev)
+        x3 = (0.5 * torch.sin(3 * tt))[:, None] + 0.6 * torch.randn(T3, N3, device=dev, generator=g3)
+        y3 = (-28 + 36 * tt)[:, None] + 0.6 * torch.randn(T3, N3, device=dev, generator=g3)
+        r3 = torch.rand(T3, N3, device=dev, generator=g3)
+        r3 = (r3 / r3.sum(dim=1, keepdim=True)).contiguous()
+        c3 = torch.empty(T3, dtype=torch.float64, device=dev)
+        d3 = torch.empty(T3, dtype=torch.float64, device=dev)
+        gx3, gy3, gr3 = torch.empty_like(x3), torch.empty_like(x3), torch.empty_like(x3)
+        m3 = torch.zeros((T3, cells), dtype=torch.int64, device=dev)
+        n3 = torch.zeros((T3, cells), dtype=torch.int32, device=dev)
+
+        def c_fwd():
+            _lib.check(L.dp_cost_coll(denv.handle, _lib.ptr(x3), _lib.ptr(y3), 1, N3, _lib.ptr(r3), 1, N3, N3, T3, 0, _lib.ptr(c3),
+                                      None, None, None, None, 0, 0, None, sp), "dp_cost_coll")
+
+        def c_bwd():
+            _lib.check(L.dp_cost_coll(denv.handle, _lib.ptr(x3), _lib.ptr(y3), 1, N3, _lib.ptr(r3), 1, N3, N3, T3, 0, _lib.ptr(c3),
+                                      None, _lib.ptr(gx3), _lib.ptr(gy3), _lib.ptr(gr3), 1, N3, None, sp), "dp_cost_coll")
+
+        def c_bin():
+            _lib.check(L.dp_bin2d_occ(ctypes.byref(spec), denv.handle, _lib.ptr(x3), _lib.ptr(y3), 1, N3, _lib.ptr(r3), 1, N3, N3,
+                                      T3, _lib.ptr(m3), _lib.ptr(n3), _lib.ptr(d3), sp), "dp_bin2d_occ")
+
+        cfg3 = {"workload": "1M weighted samples x 101 time slices (BASELINE config 3), synthetic environment 241x401x101",
+                "hbm_peak_gbs": measured_peaks()[0]["hbm_gbs"]}
+        for name, fn, nbytes in (("cost_fwd", c_fwd, 12), ("cost_fwd_bwd", c_bwd, 24), ("binning_fused_occupancy_dot", c_bin, 12)):
+            for _ in range(3):
+                fn()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(10):
+                fn()
+            a1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms = a0.elapsed_time(a1) / 10
+            ev = N3 * T3 / (ms * 1e-3)
+            cfg3[name] = {"ms": ms, "evals_per_s": ev, "algorithmic_bytes_per_eval": nbytes, "achieved_gbs": ev * nbytes / 1e9,
+                          "frac_of_hbm_peak": ev * nbytes / 1e9 / cfg3["hbm_peak_gbs"]}
+        del x3, y3, r3, gx3, gy3, gr3, m3, n3
 
     if rank != 0:
         return
@@ -388,7 +436,8 @@ def main():
                        "l2_policy": "inputs+outputs per step (%.0f MB written) exceed the 126 MB L2" % (4e-6 * Ts * 6 * N),
                        "parallelism": "samples sharded, %d rank(s); allreduce of normaliser stats, cost and int grids" % world},
             "e2e": e2e, "gpu_launches": launches["n"], "clocks": clk, "roofline": roofline,
-            "collision_cost_evals_per_s": cost_evals * world,
+            "collision_cost_evals_per_s": cfg3["cost_fwd"]["evals_per_s"] if cfg3 else cost_evals * world,
+            "collision_cost_config3": cfg3,
             "checks": {"grid_count_total": total_count, "grid_mass_total": total_mass, "cost_total": cost_total,
                        "occupancy_dot_total": float(occ_dot.sum().item())}}
     if not opts.no_cpu_baseline and world == 1:

@@ -183,15 +183,16 @@ __device__ __forceinline__ float2 as_f2(uint32_t a, uint32_t b) { return make_fl
 // One net of one tile.  NET 0 = a (w1: 12x4 matrix, 48 outputs), NET 1 = b (w2: 2x12 matrix, 24 outputs).
 // Net a runs first and leaves per z-row r: tz = tanh(z_r), A_r = g_z dz_r/dtheta, B_r = g_z dz_r/dv in sZ;
 // net b then accumulates this thread's share (rows 6h .. 6h+5) of the head sums into acc[4] = {u0, u1, du0/dtheta, du1/dv}.
-template <int NET, int TP, int TOKEN, int KC>
-__device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const float4 in, const float4 xe, float (&acc)[4]) {
-    constexpr int N3 = NET == 0 ? N3A : N3B;
+template <int TP, int TOKEN, int KC>
+__device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const float4 in, const float4 xe, float (&acc)[4]) {
+    const int N3 = NET == 0 ? N3A : N3B;
     const float *sp = c.small + NET * SMALL_NET_FLOATS;
     const uint64_t w2h = make_bdesc(c.sbase + (NET == 0 ? OFF_W2A_HI : OFF_W2B_HI), B_LBO, B_SBO);
     const uint64_t w2l = make_bdesc(c.sbase + (NET == 0 ? OFF_W2A_LO : OFF_W2B_LO), B_LBO, B_SBO);
     const uint64_t w3h = make_bdesc(c.sbase + (NET == 0 ? OFF_W3A_HI : OFF_W3B_HI), B_LBO, B_SBO);
     const uint64_t w3l = make_bdesc(c.sbase + (NET == 0 ? OFF_W3A_LO : OFF_W3B_LO), B_LBO, B_SBO);
-    constexpr uint32_t idesc128 = make_idesc(128), idesc3 = make_idesc(N3);
+    constexpr uint32_t idesc128 = make_idesc(128);
+    const uint32_t idesc3 = make_idesc(N3);
     const int h = c.h;
 
     // ---- L1: layer 1 on CUDA cores -> value operand in RA; gates g1 = 1 - h1^2 stay in registers ----------------------
@@ -602,10 +603,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
             const float ur0 = __ldg(p.uref + i), ur1 = __ldg(p.uref + T + i);
 
             float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            c.RA = R0; c.RD = R1; c.ra = R0 + lane_off; c.rd = R1 + lane_off;
-            chain<0, TP, TOKEN, KC>(c, ph, in, xe, acc);
-            c.RA = R1; c.RD = R0; c.ra = R1 + lane_off; c.rd = R0 + lane_off;
-            chain<1, TP, TOKEN, KC>(c, ph, in, xe, acc);
+#pragma unroll 1
+            for (int net = 0; net < 2; ++net) {  // net a, then net b; the two TMEM regions swap roles
+                const uint32_t A = net == 0 ? R0 : R1, Dd = net == 0 ? R1 : R0;
+                c.RA = A; c.RD = Dd; c.ra = A + lane_off; c.rd = Dd + lane_off;
+                chain<TP, TOKEN, KC>(c, ph, net, in, xe, acc);
+            }
             // exchange the partial head sums of the two feature halves (fixed order: both threads get identical totals)
             float *mine = sPart + h * 4 * TILE + c.s;
             mine[0 * TILE] = acc[0]; mine[1 * TILE] = acc[1]; mine[2 * TILE] = acc[2]; mine[3 * TILE] = acc[3];
