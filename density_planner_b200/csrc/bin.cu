@@ -26,6 +26,7 @@ struct BinArgs {
     int cx, cy;                                  // cells per axis of the output arrays
     double lo_x, hi_x, lo_y, hi_y;               // mode 1
     double scale;
+    float scale_f;  // the same power of two as a float
     const float *x, *y, *w;
     long long sx_n, sx_t, sw_n, sw_t, N;
     int Ts;
@@ -52,19 +53,25 @@ __device__ __forceinline__ int hist_bin(double v, double lo, double hi, int bins
     return k;
 }
 
+template <int MODE>
 __device__ __forceinline__ void sample_cell(const BinArgs &a, float x, float y, int &ix, int &iy) {
-    if (a.mode == 0) {
-        ix = min(max(dp_cell(x, a.q.x_lo, a.q.x_rng, a.q.r_x_rng, a.q.gxm1), 0), a.cx - 1);  // clamp to [0, G] (:261-262), cx = G+1
-        iy = min(max(dp_cell(y, a.q.y_lo, a.q.y_rng, a.q.r_y_rng, a.q.gym1), 0), a.cy - 1);
+    if (MODE == 0) {
+        ix = min(max(dp_cell<false>(x, a.q.x_lo, a.q.x_rng, a.q.r_x_rng, a.q.gxm1), 0), a.cx - 1);  // clamp to [0, G] (:261-262), cx = G+1
+        iy = min(max(dp_cell<false>(y, a.q.y_lo, a.q.y_rng, a.q.r_y_rng, a.q.gym1), 0), a.cy - 1);
     } else {
         ix = hist_bin((double)x, a.lo_x, a.hi_x, a.cx);
         iy = hist_bin((double)y, a.lo_y, a.hi_y, a.cy);
     }
 }
 
+// The int64 mass of a window cell is kept as two 32-bit words: a native 32-bit shared-memory atomic on the low word returns
+// the old value, which tells exactly whether this addition carried into the high word (a 64-bit shared atomicAdd would
+// be a compare-and-swap loop that degrades under the contention of a tight sample cloud).
+template <int MODE>
 __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
     extern __shared__ __align__(16) unsigned char bsm[];
-    unsigned long long *smass = reinterpret_cast<unsigned long long *>(bsm);
+    unsigned *slo = reinterpret_cast<unsigned *>(bsm);
+    unsigned *shi = reinterpret_cast<unsigned *>(bsm + WIN * WIN * 4);
     int *scount = reinterpret_cast<int *>(bsm + WIN * WIN * 8);
     int *sorg = reinterpret_cast<int *>(bsm + WIN * WIN * 12);
     __shared__ double shd[BIN_THREADS / 32];
@@ -84,7 +91,7 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
         int ix = 0, iy = 0, ok = 0;
         if (n_lo < n_hi) {
             const long long n = n_lo + (n_hi - n_lo) * tid / 32;
-            sample_cell(a, __ldg(xp + n * a.sx_n), __ldg(yp + n * a.sx_n), ix, iy);
+            sample_cell<MODE>(a, __ldg(xp + n * a.sx_n), __ldg(yp + n * a.sx_n), ix, iy);
             ok = (ix >= 0 && iy >= 0) ? 1 : 0;
         }
         int sx = ok ? ix : 0, sy = ok ? iy : 0, sk = ok;
@@ -101,7 +108,8 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
         }
     }
     for (int i = tid; i < WIN * WIN; i += BIN_THREADS) {
-        smass[i] = 0ull;
+        slo[i] = 0u;
+        shi[i] = 0u;
         scount[i] = 0;
     }
     __syncthreads();
@@ -116,10 +124,10 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
         if (k < span) {
             const float x = __ldg(xp + n * a.sx_n), y = __ldg(yp + n * a.sx_n);
             int ix, iy;
-            sample_cell(a, x, y, ix, iy);
+            sample_cell<MODE>(a, x, y, ix, iy);
             if (ix >= 0 && iy >= 0) {
-                const double w = wp ? (double)__ldg(wp + n * a.sw_n) : 1.0;
-                q = __double2ll_rn(w * a.scale);
+                // w * 2^s is exact in fp32 (power-of-two scale), so this equals llrint((double)w * 2^s)
+                q = wp ? __float2ll_rn(__fmul_rn(__ldg(wp + n * a.sw_n), a.scale_f)) : (long long)a.scale;
                 const int wx = ix - ox, wy = iy - oy;
                 if (wx >= 0 && wx < WIN && wy >= 0 && wy < WIN)
                     wcell = wx * WIN + wy;
@@ -129,7 +137,12 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
             }
         }
         if (wcell >= 0) {
-            if (mass) atomicAdd(smass + wcell, (unsigned long long)q);
+            if (mass) {
+                const unsigned ql = (unsigned)q, qh = (unsigned)((unsigned long long)q >> 32);
+                const unsigned old = atomicAdd(slo + wcell, ql);
+                const unsigned carry = (old + ql < old) ? 1u : 0u;
+                if (qh + carry) atomicAdd(shi + wcell, qh + carry);
+            }
             if (count) atomicAdd(scount + wcell, 1);
         }
         // samples outside the window: lanes with the same cell elect a leader that issues the global atomics for the group
@@ -154,7 +167,7 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
         const int ix = ox + wx, iy = oy + wy;
         if (ix < a.cx && iy < a.cy) {
             const long long g = (long long)ix * a.cy + iy;
-            const unsigned long long m = smass[i];
+            const unsigned long long m = ((unsigned long long)shi[i] << 32) | slo[i];
             const int c = scount[i];
             if (mass && m) atomicAdd(reinterpret_cast<unsigned long long *>(mass + g), m);
             if (count && c) atomicAdd(count + g, c);
@@ -283,6 +296,7 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
         a.lo_x = spec->lo_x; a.hi_x = spec->hi_x; a.lo_y = spec->lo_y; a.hi_y = spec->hi_y;
     }
     a.scale = ldexp(1.0, spec->mass_scale_log2);
+    a.scale_f = (float)a.scale;
     a.x = x; a.y = y; a.w = w;
     a.sx_n = sx_n; a.sx_t = sx_t; a.sw_n = sw_n; a.sw_t = sw_t; a.N = N; a.Ts = Ts;
     a.mass = mass; a.count = count;
@@ -304,10 +318,14 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
     }
     static bool attr_set = false;
     if (!attr_set) {
-        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
         attr_set = true;
     }
-    bin2d_kernel<<<dim3((unsigned)B, (unsigned)Ts), BIN_THREADS, BIN_SMEM, stream>>>(a);
+    if (a.mode == 0)
+        bin2d_kernel<0><<<dim3((unsigned)B, (unsigned)Ts), BIN_THREADS, BIN_SMEM, stream>>>(a);
+    else
+        bin2d_kernel<1><<<dim3((unsigned)B, (unsigned)Ts), BIN_THREADS, BIN_SMEM, stream>>>(a);
     DP_CUDA(cudaGetLastError());
     if (occ_dot) {
         bin_dot_finalize_kernel<<<(Ts + 127) / 128, 128, 0, stream>>>(partial, a.B, Ts, 1.0 / a.scale, occ_dot);

@@ -22,8 +22,8 @@ struct Eval {
 
 __device__ __forceinline__ Eval eval_one(const float4 *__restrict__ table, const Geom &q, int t, float x, float y, float rho,
                                          bool has_rho) {
-    int ix = dp_cell(x, q.x_lo, q.x_rng, q.r_x_rng, q.gxm1);
-    int iy = dp_cell(y, q.y_lo, q.y_rng, q.r_y_rng, q.gym1);
+    int ix = dp_cell<false>(x, q.x_lo, q.x_rng, q.r_x_rng, q.gxm1);
+    int iy = dp_cell<false>(y, q.y_lo, q.y_rng, q.r_y_rng, q.gym1);
     ix = min(max(ix, 0), q.gx - 1);  // :208-209
     iy = min(max(iy, 0), q.gy - 1);
     const float4 e = __ldg(table + ((size_t)t * q.gx + ix) * q.gy + iy);  // {p, gradX, gradY, 0}
@@ -32,8 +32,8 @@ __device__ __forceinline__ Eval eval_one(const float4 *__restrict__ table, const
     // des_gridpos = gridpos + 100 * grad ; gridpos2pos ; squared distance (:215-218), each op rounded like torch
     const float dgx = __fadd_rn(__int2float_rn(ix), __fmul_rn(100.0f, e.y));
     const float dgy = __fadd_rn(__int2float_rn(iy), __fmul_rn(100.0f, e.z));
-    const float dpx = dp_pos(dgx, q.x_lo, q.x_rng, q.gxm1, q.r_gxm1);
-    const float dpy = dp_pos(dgy, q.y_lo, q.y_rng, q.gym1, q.r_gym1);
+    const float dpx = dp_pos<false>(dgx, q.x_lo, q.x_rng, q.gxm1, q.r_gxm1);
+    const float dpy = dp_pos<false>(dgy, q.y_lo, q.y_rng, q.gym1, q.r_gym1);
     const float ex = __fsub_rn(dpx, x), ey = __fsub_rn(dpy, y);
     const float sq = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
     const float w = has_rho ? __fmul_rn(rho, e.x) : e.x;
@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(CB) cost_nfast_kernel(CostArgs a) {
 
 // (V) the same for 16-byte aligned rows: every thread evaluates four consecutive samples per iteration from three LDG.128
 // (x, y, rho) and writes the gradients with STG.128 -- a quarter of the memory instructions of (A) for the same bytes.
-__global__ void __launch_bounds__(CB) cost_vec4_kernel(CostArgs a) {
+template <bool WANT_G>
+__global__ void __launch_bounds__(CB, WANT_G ? 4 : 6) cost_vec4_kernel(CostArgs a) {
     __shared__ double shd[CB / 32];
     __shared__ float shf[CB / 32];
     const int t = blockIdx.y;
@@ -141,7 +142,6 @@ __global__ void __launch_bounds__(CB) cost_vec4_kernel(CostArgs a) {
     const float *xp = a.x + (long long)t * a.sx_t;
     const float *yp = a.y + (long long)t * a.sx_t;
     const float *rp = has_rho ? a.rho + (long long)t * a.sr_t : nullptr;
-    const bool want_g = a.gx != nullptr;
     double acc = 0.0;
     float mx = -INFINITY;
     const long long n4 = a.N >> 2;  // full groups of four
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(CB) cost_vec4_kernel(CostArgs a) {
         if (e1.active) mx = fmaxf(mx, e1.term);
         if (e2.active) mx = fmaxf(mx, e2.term);
         if (e3.active) mx = fmaxf(mx, e3.term);
-        if (want_g) {
+        if (WANT_G) {
             const long long o = (long long)t * a.sg_t;
             reinterpret_cast<float4 *>(a.gx + o)[g] = make_float4(e0.gx, e1.gx, e2.gx, e3.gx);
             reinterpret_cast<float4 *>(a.gy + o)[g] = make_float4(e0.gy, e1.gy, e2.gy, e3.gy);
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(CB) cost_vec4_kernel(CostArgs a) {
         const Eval e = eval_one(a.table, a.q, t, __ldg(xp + n), __ldg(yp + n), has_rho ? __ldg(rp + n) : 0.0f, has_rho);
         acc += (double)e.term;
         if (e.active) mx = fmaxf(mx, e.term);
-        if (want_g) {
+        if (WANT_G) {
             const long long o = n + (long long)t * a.sg_t;
             a.gx[o] = e.gx;
             a.gy[o] = e.gy;
@@ -371,8 +371,17 @@ int dp_cost_coll(const dp_env *e, const float *x, const float *y, int64_t sx_n, 
         auto al16 = [](const void *p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
         const bool vec = al16(x) && al16(y) && al16(rho) && al16(gx) && al16(gy) && al16(grho) && (sx_t % 4 == 0) &&
                          (!rho || sr_t % 4 == 0) && (!gx || sg_t % 4 == 0);
-        if (vec)
-            cost_vec4_kernel<<<dim3((unsigned)B, (unsigned)Ts), CB, 0, stream>>>(a);
+        if (vec) {
+            // two full waves of resident blocks over all slices (the kernel strides over the samples of its slice)
+            long long Bv = (2LL * (gx ? 4 : 6) * 148) / Ts;
+            if (Bv < 1) Bv = 1;
+            if (Bv > B) Bv = B;
+            a.B = (int)Bv;
+            if (gx)
+                cost_vec4_kernel<true><<<dim3((unsigned)Bv, (unsigned)Ts), CB, 0, stream>>>(a);
+            else
+                cost_vec4_kernel<false><<<dim3((unsigned)Bv, (unsigned)Ts), CB, 0, stream>>>(a);
+        }
         else
             cost_nfast_kernel<<<dim3((unsigned)B, (unsigned)Ts), CB, 0, stream>>>(a);
     } else {

@@ -114,14 +114,13 @@ void dp_tc_release(dp_controller *c);
 
 // ---- small device helpers ----------------------------------------------------------------------------------
 // Correctly rounded a / b without the branchy IEEE division sequence: q = RN(a * RN(1/b)), one exact FMA residual and one
-// FMA correction (Markstein).  Checked exhaustively against `a / b` for b in {24, 40, 240, 400} and every float with
-// 2^-20 <= |a| <= 2^10; outside that range (and for a == 0) the IEEE division is used.
+// FMA correction (Markstein).  Checked exhaustively against `a / b` for b in {24, 40, 240, 400} over ALL finite floats a:
+// the only mismatches have |a| < 1.9e-37 (subnormal intermediate products); below 1e-30 the IEEE division is used.
 __device__ __forceinline__ float dp_div(float a, float b, float rb) {
     const float q = __fmul_rn(a, rb);
     const float r = __fmaf_rn(-q, b, a);
     const float q1 = __fmaf_rn(r, rb, q);
-    const float aa = fabsf(a);
-    return (aa >= 9.5367431640625e-07f && aa <= 1024.0f) ? q1 : __fdiv_rn(a, b);
+    return (fabsf(a) >= 1e-30f || a == 0.0f) ? q1 : __fdiv_rn(a, b);
 }
 
 // grid geometry with the reciprocals dp_div needs (hyperparams.py:124,154-155)
@@ -147,12 +146,23 @@ inline DpGeom dp_make_geom(const dp_grid_geom &g) {
     return q;
 }
 
+// The same without the guard, for the hot kernels: a mismatch needs 0 < |a| < 1.9e-37, i.e. a sample within 1e-37 m of the
+// grid's lower edge (the cell index rounds to 0 either way) or a gradient-shifted grid position of that magnitude
+// (the position then equals the lower edge either way unless that edge is exactly 0).
+__device__ __forceinline__ float dp_div_fast(float a, float b, float rb) {
+    const float q = __fmul_rn(a, rb);
+    return __fmaf_rn(__fmaf_rn(-q, b, a), rb, q);
+}
+
 // pos2gridpos for one coordinate, fp32 op for op as torch evaluates motion_planning/utils.py:82-85
+template <bool GUARD = true>
 __device__ __forceinline__ int dp_cell(float p, float lo, float range, float r_range, float gm1) {
-    float q = __fmul_rn(dp_div(__fsub_rn(p, lo), range, r_range), gm1);
+    const float a = __fsub_rn(p, lo);
+    const float q = __fmul_rn(GUARD ? dp_div(a, range, r_range) : dp_div_fast(a, range, r_range), gm1);
     return __float2int_rn(__fadd_rn(q, 0.001f));  // round-half-even like torch.round; values are far from int overflow
 }
 // gridpos2pos for one coordinate (motion_planning/utils.py:100-116)
+template <bool GUARD = true>
 __device__ __forceinline__ float dp_pos(float g, float lo, float range, float gm1, float r_gm1) {
-    return __fadd_rn(__fmul_rn(dp_div(g, gm1, r_gm1), range), lo);
+    return __fadd_rn(__fmul_rn(GUARD ? dp_div(g, gm1, r_gm1) : dp_div_fast(g, gm1, r_gm1), range), lo);
 }
