@@ -199,6 +199,11 @@ def main():
     if opts.impl == "reference":
         return run_reference_arm(opts)
 
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import density_planner_b200 as dp
     from density_planner_b200 import _lib, dist as D, grid as G
@@ -443,7 +448,8 @@ def main():
     if not opts.no_cpu_baseline and world == 1:
         base, _, _ = cpu_oracle_rate()
         line["cpu_baseline"] = base
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
