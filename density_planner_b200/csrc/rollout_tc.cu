@@ -64,7 +64,8 @@ static_assert(SP_C1H + 64 == SMALL_NET_FLOATS, "small block layout");
 // shared memory behind the image
 constexpr int OFF_Z = IMAGE_BYTES;                              // float [2 groups][36][128]: tz, A, B per z-row
 constexpr int OFF_PART = OFF_Z + NGROUPS * 36 * TILE * 4;       // float [2 groups][2 halves][4][128]
-constexpr int OFF_BAR = OFF_PART + NGROUPS * 2 * 4 * TILE * 4;  // 2 mbarriers + tmem pointer
+constexpr int OFF_CB = OFF_PART + NGROUPS * 2 * 4 * TILE * 4;   // float4 [2 groups][2 nets][64 pairs]: {wz_j, wz_j1, cb_j, cb_j1}
+constexpr int OFF_BAR = OFF_CB + NGROUPS * 2 * 64 * 16;         // 2 mbarriers + tmem pointer
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -93,6 +94,7 @@ struct Ctx {
     bool leader;        // first warp of the group: issues the MMAs
     const float *small; // fp32 blocks of both nets
     float *sZ;          // this group's [36][128]
+    const float4 *sCB;  // this group's [2 nets][64 pairs] {wz pair, per-step constant pair} (see the step loop)
 };
 
 __device__ __forceinline__ void group_sync(int bar_id) { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GT) : "memory"); }
@@ -209,9 +211,8 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     uint32_t g1[32];
     {
         const float4 *W1P = reinterpret_cast<const float4 *>(sp + SP_W1P);
-        const float2 *B1P = reinterpret_cast<const float2 *>(sp + SP_B1P);
-        const float2 ix = make_float2(in.x, in.x), iy = make_float2(in.y, in.y), iz = make_float2(in.z, in.z),
-                     iw = make_float2(in.w, in.w);
+        const float4 *CB = c.sCB + NET * 64;
+        const float2 ix = make_float2(in.x, in.x), iy = make_float2(in.y, in.y), iz = make_float2(in.z, in.z);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int ch = 4 * h + i;
@@ -222,18 +223,17 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int pair = 8 * ch + pq + e;
-                    const float4 wa = W1P[2 * pair], wb = W1P[2 * pair + 1];
-                    y[e] = __ffma2_rn(make_float2(wa.x, wa.y), ix, B1P[pair]);
+                    const float4 wa = W1P[2 * pair], wc = CB[pair];  // wc.zw = W1[:,3] * in.w + b1 (the same for every sample)
+                    y[e] = __ffma2_rn(make_float2(wa.x, wa.y), ix, make_float2(wc.z, wc.w));
                     y[e] = __ffma2_rn(make_float2(wa.z, wa.w), iy, y[e]);
-                    y[e] = __ffma2_rn(make_float2(wb.x, wb.y), iz, y[e]);
-                    y[e] = __ffma2_rn(make_float2(wb.z, wb.w), iw, y[e]);
+                    y[e] = __ffma2_rn(make_float2(wc.x, wc.y), iz, y[e]);
                 }
-                float2 t[2], g[2];
-                tanh_gate4(y[0], y[1], t[0], t[1], g[0], g[1]);
+                float2 t[2];
+                tanh4(y[0], y[1], t[0], t[1]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     split_h2(t[e], av[pq + e], av[8 + pq + e]);
-                    g1[8 * i + pq + e] = pack_h2(g[e].x, g[e].y);
+                    g1[8 * i + pq + e] = gate_of(t[e], av[pq + e]);
                 }
             }
             st16(c.ra + 16 * ch, av);
@@ -269,12 +269,12 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
             for (int pq = 0; pq < 8; pq += 2) {
                 const float2 y0 = __ffma2_rn(as_f2(d[2 * pq], d[2 * pq + 1]), cs, B2P[8 * ch + pq]);
                 const float2 y1 = __ffma2_rn(as_f2(d[2 * pq + 2], d[2 * pq + 3]), cs, B2P[8 * ch + pq + 1]);
-                float2 t[2], g[2];
-                tanh_gate4(y0, y1, t[0], t[1], g[0], g[1]);
+                float2 t[2];
+                tanh4(y0, y1, t[0], t[1]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     split_h2(t[e], av[pq + e], av[8 + pq + e]);
-                    gs[8 * i + pq + e] = pack_h2(g[e].x, g[e].y);
+                    gs[8 * i + pq + e] = gate_of(t[e], av[pq + e]);
                 }
             }
             st16(c.rd + 16 * ch, av);
@@ -523,6 +523,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
     c.leader = wl == 0;
     c.small = reinterpret_cast<const float *>(smem + OFF_SMALL);
     c.sZ = reinterpret_cast<float *>(smem + OFF_Z) + grp * 36 * TILE;
+    c.sCB = reinterpret_cast<const float4 *>(smem + OFF_CB) + grp * 2 * 64;
     c.who = (warp == 0) ? 0 : (warp == 7) ? 1 : (warp == 8) ? 2 : (warp == 15) ? 3 : -1;
     c.trace = (p.trace && blockIdx.x == 0 && lane == 0 && c.who >= 0) ? p.trace : nullptr;
     c.tchain = 0;
@@ -539,6 +540,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
 
     // both groups run the same number of chains (a group without a tile in the last round runs a dummy one: the token
     // hand-off is symmetric)
+    // per-step constant part of the layer-1 pre-activation, W1[:,3] * in.w + b1 (in.w = xref[3][t] is the same for every
+    // sample): thread k of the group owns (net k / 128, feature k % 128) and refreshes it once per step
+    float *cb_mine;
+    float cb_w, cb_b;
+    {
+        const int k = tid & (GT - 1), net = k >> 7, j = k & 127;
+        const float *spn = c.small + net * SMALL_NET_FLOATS;
+        float *cb4 = reinterpret_cast<float *>(smem + OFF_CB) + ((grp * 2 + net) * 64 + (j >> 1)) * 4;
+        cb4[j & 1] = spn[SP_W1P + 8 * (j >> 1) + 4 + (j & 1)];  // W1[:,2] pair, static
+        cb_mine = cb4 + 2 + (j & 1);
+        cb_w = spn[SP_W1P + 8 * (j >> 1) + 6 + (j & 1)];
+        cb_b = spn[SP_B1P + j];
+    }
     const long long num_rounds = (num_tiles + NGROUPS - 1) / NGROUPS;
     for (long long round = blockIdx.x; round < num_rounds; round += gridDim.x) {
         const long long tile = round * NGROUPS + grp;
@@ -554,6 +568,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
         st.rho = p.rho0 ? __ldg(p.rho0 + nl) : (logd ? 0.0f : 1.0f);
         st.margin = 1e30f;
         int next_store = 0, slot = 0;
+        if (T > 0) {
+            *cb_mine = fmaf(cb_w, __ldg(p.xref + 3 * T1), cb_b);
+            group_sync(c.bar_id);
+        }
         for (int i = 0;; ++i) {
             const float xr0 = __ldg(p.xref + 0 * T1 + i), xr1 = __ldg(p.xref + 1 * T1 + i);
             const float xr2 = __ldg(p.xref + 2 * T1 + i), xr3 = __ldg(p.xref + 3 * T1 + i);
@@ -612,6 +630,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
             // exchange the partial head sums of the two feature halves (fixed order: both threads get identical totals)
             float *mine = sPart + h * 4 * TILE + c.s;
             mine[0 * TILE] = acc[0]; mine[1 * TILE] = acc[1]; mine[2 * TILE] = acc[2]; mine[3 * TILE] = acc[3];
+            if (i + 1 < T) *cb_mine = fmaf(cb_w, __ldg(p.xref + 3 * T1 + i + 1), cb_b);  // every thread is past both L1 stages
             fence_before();
             group_sync(c.bar_id);
             const float *p0 = sPart + c.s, *p1 = sPart + 4 * TILE + c.s;

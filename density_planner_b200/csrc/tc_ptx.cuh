@@ -158,7 +158,7 @@ __device__ __forceinline__ float2 copysign2(const float2 mag, const float2 sgn) 
     return make_float2(__uint_as_float(__float_as_uint(mag.x) | (__float_as_uint(sgn.x) & 0x80000000u)),
                        __uint_as_float(__float_as_uint(mag.y) | (__float_as_uint(sgn.y) & 0x80000000u)));
 }
-__device__ __forceinline__ void tanh_gate4(const float2 yA, const float2 yB, float2 &tA, float2 &tB, float2 &gA, float2 &gB) {
+__device__ __forceinline__ void tanh4(const float2 yA, const float2 yB, float2 &tA, float2 &tB) {
     const float2 one = make_float2(1.0f, 1.0f), two = make_float2(2.0f, 2.0f), mone = make_float2(-1.0f, -1.0f);
     const float2 aA = __fadd2_rn(make_float2(ex2_negabs(yA.x), ex2_negabs(yA.y)), one);
     const float2 aB = __fadd2_rn(make_float2(ex2_negabs(yB.x), ex2_negabs(yB.y)), one);
@@ -166,11 +166,8 @@ __device__ __forceinline__ void tanh_gate4(const float2 yA, const float2 yB, flo
     const float R = rcp_approx(p.x * p.y);
     const float2 q = make_float2(R * p.y, R * p.x);            // (1/(a0 a2), 1/(a1 a3))
     const float2 rA = __fmul2_rn(q, aB), rB = __fmul2_rn(q, aA);  // (1/a0, 1/a1), (1/a2, 1/a3)
-    const float2 mA = __ffma2_rn(two, rA, mone), mB = __ffma2_rn(two, rB, mone);  // tanh|x|
-    gA = __ffma2_rn(make_float2(-mA.x, -mA.y), mA, one);
-    gB = __ffma2_rn(make_float2(-mB.x, -mB.y), mB, one);
-    tA = copysign2(mA, yA);
-    tB = copysign2(mB, yB);
+    tA = copysign2(__ffma2_rn(two, rA, mone), yA);
+    tB = copysign2(__ffma2_rn(two, rB, mone), yB);
 }
 __device__ __forceinline__ uint32_t h2_bits(const __half2 h) { return *reinterpret_cast<const uint32_t *>(&h); }
 __device__ __forceinline__ __half2 bits_h2(const uint32_t u) { return *reinterpret_cast<const __half2 *>(&u); }
@@ -182,6 +179,25 @@ __device__ __forceinline__ void split_h2(const float2 v, uint32_t &hi, uint32_t 
     const float2 d = __fadd2_rn(v, make_float2(-f.x, -f.y));
     hi = h2_bits(h);
     lo = pack_h2(d.x, d.y);
+}
+// tanh gate 1 - t^2 of a packed fp16 pair, one HFMA2 (the gates only scale the fp16 tangent operands)
+__device__ __forceinline__ uint32_t gate_h2(const uint32_t hi) {
+    const __half2 h = bits_h2(hi);
+    return h2_bits(__hfma2(__hneg2(h), h, __floats2half2_rn(1.0f, 1.0f)));
+}
+
+// the gate used by the kernel: fp32 (FFMA2 + F2FP) by default; -DDP_GATE_FROM_HI=1 forms it from the fp16 hi pair (one
+// instruction less per feature pair, but the log-density error grows from 0.22 to 0.36 of its tolerance)
+#ifndef DP_GATE_FROM_HI
+#define DP_GATE_FROM_HI 0
+#endif
+__device__ __forceinline__ uint32_t gate_of(const float2 t, const uint32_t hi) {
+#if DP_GATE_FROM_HI
+    return gate_h2(hi);
+#else
+    const float2 g = __ffma2_rn(make_float2(-t.x, -t.y), t, make_float2(1.0f, 1.0f));
+    return pack_h2(g.x, g.y);
+#endif
 }
 
 // ---- host: canonical no-swizzle K-major image of W [n_rows][128] (rows >= n_valid are zero) --------------------------------
