@@ -237,9 +237,16 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                 }
             }
             st16(c.ra + 16 * ch, av);
-            if (KC)
+            if (KC == 1)
                 chunk_issue(c, i, i == 3, [&] {
                     mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, i, i == 0);
+                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 4 + i, false);
+                });
+            if (KC == 2 && (i & 1))  // two batches of four K-chunks
+                chunk_issue(c, i, i == 3, [&] {
+                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, i - 1, i == 1);
+                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, i, false);
+                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 3 + i, false);
                     mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 4 + i, false);
                 });
         }
@@ -279,9 +286,16 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
             }
             st16(c.rd + 16 * ch, av);
             st8(c.ra + 8 * ch, &g1[8 * i]);
-            if (KC)
+            if (KC == 1)
                 chunk_issue(c, i, i == 3, [&] {
                     mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, i, i == 0);
+                    mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, 4 + i, false);
+                });
+            if (KC == 2 && (i & 1))
+                chunk_issue(c, i, i == 3, [&] {
+                    mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, i - 1, i == 1);
+                    mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, i, false);
+                    mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, 3 + i, false);
                     mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, 4 + i, false);
                 });
         }
@@ -357,17 +371,28 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int ch = 4 * h + i;
-            uint32_t at0[8], at1[8];
+            uint32_t at0[8], at1[8], k0[8], k1[8];
+            *reinterpret_cast<uint4 *>(k0) = *reinterpret_cast<const uint4 *>(c0h + 8 * ch);
+            *reinterpret_cast<uint4 *>(k0 + 4) = *reinterpret_cast<const uint4 *>(c0h + 8 * ch + 4);
+            *reinterpret_cast<uint4 *>(k1) = *reinterpret_cast<const uint4 *>(c1h + 8 * ch);
+            *reinterpret_cast<uint4 *>(k1 + 4) = *reinterpret_cast<const uint4 *>(c1h + 8 * ch + 4);
 #pragma unroll
             for (int pq = 0; pq < 8; ++pq) {
-                at0[pq] = h2_bits(__hmul2(bits_h2(gst[8 * i + pq]), bits_h2(c0h[8 * ch + pq])));
-                at1[pq] = h2_bits(__hmul2(bits_h2(gst[8 * i + pq]), bits_h2(c1h[8 * ch + pq])));
+                at0[pq] = h2_bits(__hmul2(bits_h2(gst[8 * i + pq]), bits_h2(k0[pq])));
+                at1[pq] = h2_bits(__hmul2(bits_h2(gst[8 * i + pq]), bits_h2(k1[pq])));
             }
             st8(c.rd + 8 * ch, at0);
             st8(c.rd + 64 + 8 * ch, at1);
-            if (KC)  // every thread reaches its first arrival after all its reads of RA (outputs, parked gates) completed
+            if (KC == 1)  // every thread reaches its first arrival after all its reads of RA (outputs, parked gates) completed
                 chunk_issue(c, i, i == 3, [&] {
                     mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, i, i == 0);
+                    mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, 4 + i, false);
+                });
+            if (KC == 2 && (i & 1))
+                chunk_issue(c, i, i == 3, [&] {
+                    mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, i - 1, i == 1);
+                    mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, i, false);
+                    mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, 3 + i, false);
                     mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, 4 + i, false);
                 });
         }
@@ -704,12 +729,13 @@ int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStr
     static int variant = -1;  // tuning / A-B knob: DP_TC_VARIANT = 100 * k_chunked + 10 * tangent_products + token
     typedef void (*kern_t)(RolloutParams);
     static const kern_t kerns[8] = {rollout_tc_kernel<1, 0, 0>, rollout_tc_kernel<1, 1, 0>, rollout_tc_kernel<2, 0, 0>,
-                                    rollout_tc_kernel<2, 1, 0>, rollout_tc_kernel<1, 0, 1>, rollout_tc_kernel<1, 1, 1>,
-                                    rollout_tc_kernel<2, 0, 1>, rollout_tc_kernel<2, 1, 1>};
+                                    rollout_tc_kernel<2, 1, 0>, rollout_tc_kernel<1, 0, 1>, rollout_tc_kernel<1, 0, 2>,
+                                    rollout_tc_kernel<2, 0, 1>, rollout_tc_kernel<2, 0, 2>};
     if (variant < 0) {
         const char *e = getenv("DP_TC_VARIANT");
-        const int v = e ? atoi(e) : 110;
-        variant = ((v / 100) ? 4 : 0) + (((v / 10) % 10 == 1) ? 0 : 2) + ((v % 10) ? 1 : 0);
+        const int v = e ? atoi(e) : 110;  // 100 * K-chunking (0 off, 1 four batches, 2 two batches) + 10 * tangent products + token
+        const int kc = v / 100, tp2 = ((v / 10) % 10 == 1) ? 0 : 2;
+        variant = kc == 0 ? tp2 + ((v % 10) ? 1 : 0) : 4 + tp2 + (kc == 2 ? 1 : 0);
     }
     if (!attr_set[c->device & 63]) {
         for (int k = 0; k < 8; ++k)
