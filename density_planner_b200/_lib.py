@@ -50,6 +50,11 @@ _SIGNATURES = {
                             _i64, _vp, _vp]),
     "dp_bin2d": (_int, [ctypes.POINTER(BinSpec), _vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp]),
     "dp_bin2d_occ": (_int, [ctypes.POINTER(BinSpec), _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
+    "dp_xref_traj": (_int, [_vp, _int, _vp, _f32, _int, _int, _vp, _vp]),
+    "dp_xref_traj_bwd": (_int, [_vp, _vp, _f32, _int, _int, _vp, _vp, _vp]),
+    "dp_cost_state": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
+    "dp_cost_state_bwd": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _f32, _f32, _f32, _vp,
+                                 _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
     "dp_normalize_stats": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
     "dp_normalize_apply": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp]),
     "dp_probe_ffma_peak": (_int, [_int, ctypes.POINTER(ctypes.c_double)]),

@@ -362,3 +362,81 @@ def get_cost_coll_initialize(x_traj, denv):
         x, y = x.contiguous(), y.contiguous()
     _, samples, _, _, _ = _cost_call(denv, x, y, None, False, False, True)
     return samples.to(dtype=torch.float32, device=x_traj.device)
+
+
+# ---- goal / bounds cost terms of MotionPlanner.get_cost --------------------------------------
+class _StateCost(torch.autograd.Function):
+    """dp_cost_state / dp_cost_state_bwd on (N,5,Ts) x and (N,1,Ts) rho (any strides, CUDA tensors)."""
+
+    @staticmethod
+    def forward(ctx, x, rho, lo5, hi5, goal_xy, get_max):
+        L = _lib.lib()
+        dev = x.device
+        N, _, Ts = x.shape
+        xd = x.detach()
+        rd = rho.detach()
+        out = torch.empty(3, dtype=torch.float64, device=dev)
+        flags = torch.empty(2, dtype=torch.int32, device=dev)
+        lo = (ctypes.c_float * 5)(*[float(v) for v in lo5])
+        hi = (ctypes.c_float * 5)(*[float(v) for v in hi5])
+        goal = (ctypes.c_float * 2)(float(goal_xy[0]), float(goal_xy[1]))
+        with torch.cuda.device(dev):
+            _lib.check(L.dp_cost_state(_lib.ptr(xd), xd.stride(0), xd.stride(1), xd.stride(2), _lib.ptr(rd), rd.stride(0),
+                                       rd.stride(2), N, Ts, lo, hi, goal, 1 if get_max else 0, _lib.ptr(out), _lib.ptr(flags),
+                                       _lib.current_stream(dev)), "dp_cost_state")
+        ctx.save_for_backward(xd, rd)
+        ctx.consts = (lo, hi, goal, get_max)
+        ctx.mark_non_differentiable(flags)
+        return out.to(torch.float32), flags
+
+    @staticmethod
+    def backward(ctx, g_out, _g_flags):
+        xd, rd = ctx.saved_tensors
+        lo, hi, goal, get_max = ctx.consts
+        if get_max:
+            raise RuntimeError("the max variants of the goal / bounds costs are evaluation-only (as in the reference)")
+        L = _lib.lib()
+        dev = xd.device
+        N, _, Ts = xd.shape
+        gx = torch.empty((N, 5, Ts), dtype=torch.float32, device=dev)
+        gr = torch.empty((N, 1, Ts), dtype=torch.float32, device=dev)
+        s = [float(v) for v in g_out.detach().cpu()]
+        with torch.cuda.device(dev):
+            _lib.check(L.dp_cost_state_bwd(_lib.ptr(xd), xd.stride(0), xd.stride(1), xd.stride(2), _lib.ptr(rd), rd.stride(0),
+                                           rd.stride(2), N, Ts, lo, hi, goal, s[0], s[1], s[2], _lib.ptr(gx), gx.stride(0),
+                                           gx.stride(1), gx.stride(2), _lib.ptr(gr), gr.stride(0), gr.stride(2),
+                                           _lib.current_stream(dev)), "dp_cost_state_bwd")
+        return gx, gr, None, None, None, None
+
+
+def state_costs(x_traj, rho_traj, lo5, hi5, goal_xy, get_max=False):
+    """Raw goal / bounds terms: returns (terms, flags) with terms = [goal, below-bound part, above-bound part] (float32,
+    differentiable w.r.t. x_traj and rho_traj in sum mode) and flags = [any x < lo, any x > hi] over state dims 0..3."""
+    dev = _cuda_device(x_traj)
+    x = x_traj.to(device=dev, dtype=torch.float32)
+    rho = rho_traj.to(device=dev, dtype=torch.float32)
+    if rho.shape[2] < x.shape[2]:
+        raise ValueError("rho_traj has fewer time points than x_traj")
+    return _StateCost.apply(x, rho[:, :, :x.shape[2]] if rho.shape[2] != x.shape[2] else rho, lo5, hi5, goal_xy, bool(get_max))
+
+
+def get_cost_goal(x_traj, rho_traj, xrefN, args, evaluate=False, get_max=False):
+    """MotionPlanner.get_cost_goal (motion_planning/MotionPlanner.py:121-147) on the kernels."""
+    big = [float("inf")] * 5
+    terms, _ = state_costs(x_traj, rho_traj, [-v for v in big], big, (float(xrefN[0, 0, 0]), float(xrefN[0, 1, 0])), get_max)
+    cost_goal = terms[0]
+    close = cost_goal < args.close2goal_thr
+    if not evaluate and not bool(close):
+        cost_goal = cost_goal * args.weight_goal_far
+    return cost_goal.to(x_traj.device), close.to(x_traj.device)
+
+
+def get_cost_bounds(x_traj, rho_traj, system, evaluate=False, get_max=False):
+    """MotionPlanner.get_cost_bounds (motion_planning/MotionPlanner.py:149-190) on the kernels: returns (cost (1,), in_bounds)."""
+    x_min, x_max = (system.X_MIN, system.X_MAX) if evaluate else (system.X_MIN_MP, system.X_MAX_MP)
+    terms, flags = state_costs(x_traj, rho_traj, x_min[0, :, 0].tolist(), x_max[0, :, 0].tolist(), (0.0, 0.0), get_max)
+    f = flags.cpu()
+    # the reference enters a part only if a bound is violated in the first four state dimensions (:173,:181)
+    cost = terms[1] * float(f[0] != 0) + terms[2] * float(f[1] != 0)
+    in_bounds = torch.tensor(bool(f[0] == 0 and f[1] == 0))
+    return cost.reshape(1).to(x_traj.device), in_bounds

@@ -13,7 +13,8 @@ def default_args(**overrides):
         path_rawdata="data/rawdata/2022-07-12_discr10_train/",
         mp_sample_size=500, mp_sampling="random", mp_gaussians=5,
         environment_size=[-12, 12, -30, 10], grid_wide=0.1,
-        weight_coll=1e-1,
+        weight_coll=1e-1, weight_goal=1e-2, weight_uref=1e-4, weight_bounds=1e1,          # hyperparams.py:136-139
+        weight_goal_far=10.0, weight_uref_effort=1e-2, close2goal_thr=3.0,                 # hyperparams.py:107-109
     )
     for k, v in overrides.items():
         setattr(a, k, v)

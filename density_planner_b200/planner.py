@@ -71,8 +71,9 @@ class CollisionCost:
 
 def attach(planner, device=None):
     """Bind the kernel-backed calls into a reference planner object in place:
-    `planner.get_cost_coll`, `planner.get_cost_coll_initialize` (if present) and the LE branch of
-    `planner.ego.predict_density`.  The planner's Python optimisation loop is unchanged."""
+    `planner.get_cost_coll`, `planner.get_cost_coll_initialize` (if present), `planner.get_cost_goal`,
+    `planner.get_cost_bounds`, the LE branch of `planner.ego.predict_density` and `ego.system.up2ref_traj` (forward and
+    analytic backward in one launch each).  The planner's Python optimisation loop is unchanged."""
     from .systems import Car
 
     ego = planner.ego
@@ -96,5 +97,26 @@ def attach(planner, device=None):
         return pred.predict_density(up, xref_traj, use_nn=False, xe0=xe0, rho0=rho0, compute_density=compute_density)
 
     ego.predict_density = _predict
+
+    # goal / bounds terms (MotionPlanner.py:121-190) and the reference-trajectory integrator (ControlAffineSystem.py:370):
+    # same signatures, tensors come back on the caller's device with autograd intact
+    def _goal(x_traj, rho_traj, evaluate=False, get_max=False):
+        if rho_traj is None:
+            return goal_ref(x_traj, rho_traj, evaluate=evaluate, get_max=get_max)
+        return _grid.get_cost_goal(x_traj, rho_traj, ego.xrefN, ego.args, evaluate=evaluate, get_max=get_max)
+
+    def _bounds(x_traj, rho_traj, evaluate=False, get_max=False):
+        return _grid.get_cost_bounds(x_traj, rho_traj, system, evaluate=evaluate, get_max=get_max)
+
+    goal_ref = planner.get_cost_goal
+    planner.get_cost_goal = _goal
+    planner.get_cost_bounds = _bounds
+    dev = system.controller.controller.device
+
+    def _up2ref(xref0, up, args, short=True):
+        uref_traj, xref_traj = system.up2ref_traj(xref0.to(dev), up.to(dev), args, short=short)
+        return uref_traj.to(up.device), xref_traj.to(up.device)
+
+    ego.system.up2ref_traj = _up2ref
     planner._dp_b200 = (cc, pred)
     return planner

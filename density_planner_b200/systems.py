@@ -42,6 +42,44 @@ class Controller:
         return _step(self.controller, x, xref, uref, want=("u",))["u"]
 
 
+class _XrefTraj(torch.autograd.Function):
+    """dp_xref_traj / dp_xref_traj_bwd: xref0 (B or 1, 5, 1), uref (B, 2, T) on the GPU -> xref (B, 5, T+1)."""
+
+    @staticmethod
+    def forward(ctx, xref0, uref, dt):
+        L = _lib.lib()
+        B, _, T = uref.shape
+        dev = uref.device
+        batched = xref0.shape[0] == B and B > 1
+        x0 = xref0.detach().to(torch.float32).reshape(-1, 5).contiguous()
+        if not batched:
+            x0 = x0[:1].contiguous()
+        u = uref.detach().to(torch.float32).contiguous()
+        out = torch.empty((B, 5, T + 1), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.dp_xref_traj(_lib.ptr(x0), 1 if batched else 0, _lib.ptr(u), dt, B, T, _lib.ptr(out),
+                                      _lib.current_stream(dev)), "dp_xref_traj")
+        ctx.save_for_backward(out)
+        ctx.dt, ctx.x0_shape, ctx.batched = dt, xref0.shape, batched
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (xref,) = ctx.saved_tensors
+        L = _lib.lib()
+        B, _, T1 = xref.shape
+        T = T1 - 1
+        dev = xref.device
+        g = g.to(torch.float32).contiguous()
+        gu = torch.empty((B, 2, T), dtype=torch.float32, device=dev)
+        gx0 = torch.empty((B, 5), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.dp_xref_traj_bwd(_lib.ptr(xref), _lib.ptr(g), ctx.dt, B, T, _lib.ptr(gu), _lib.ptr(gx0),
+                                          _lib.current_stream(dev)), "dp_xref_traj_bwd")
+        gx0 = gx0.reshape(ctx.x0_shape) if ctx.batched else gx0.sum(dim=0).reshape(ctx.x0_shape)
+        return gx0, gu, None
+
+
 def _step(dc, x, xref, uref, want):
     """One evaluation of the closed loop for N states sharing (xref, uref) -> dict of tensors on x's device."""
     L = _lib.lib()
@@ -146,8 +184,14 @@ class ControlAffineSystem:
         return (self.XREF0_MAX - self.XREF0_MIN) * torch.rand(1, self.DIM_X, 1) + self.XREF0_MIN
 
     def compute_xref_traj(self, xref0, uref_traj, args, short=False):
-        """Open-loop Euler integration of the reference (:341-354)."""
+        """Open-loop Euler integration of the reference (:341-354).
+
+        CUDA inputs run in one kernel launch with an analytic (discrete adjoint) backward; CPU inputs keep the reference's
+        torch loop, which the seeded sampling paths (`get_valid_ref`) rely on for bit-identical rejection decisions."""
         n_sim = min(args.N_sim, uref_traj.shape[2] + 1)
+        if uref_traj.is_cuda:
+            xref_traj = _XrefTraj.apply(xref0.to(uref_traj.device), uref_traj[:, :, :n_sim - 1], float(args.dt_sim))
+            return xref_traj[:, :, ::args.factor_pred] if short else xref_traj
         states = [xref0]
         for i in range(n_sim - 1):
             states.append(self.get_next_xref(states[-1], uref_traj[:, :, [i]], args.dt_sim))

@@ -181,6 +181,37 @@ int dp_normalize_stats(const float *rholog, const float *rho0, int64_t N, int Ts
 int dp_normalize_apply(const float *rholog, const float *rho0, int64_t N, int Ts, int64_t ldn, const float *lmax,
                        const double *lsum, float *rho, void *stream);
 
+/*
+ * Reference-trajectory integrator: ControlAffineSystem.compute_xref_traj
+ * (systems/ControlAffineSystem.py:341-354, get_next_xref :130-134) for B trajectories, and the gradient of a scalar loss
+ * w.r.t. the reference inputs and the start state (what autograd computes through up2ref_traj :370-379).
+ *   xref0 dev [B][5] (xref0_batched != 0) or [5] shared by all trajectories;  uref dev [B][2][T];  xref dev [B][5][T+1]
+ *   gxref dev [B][5][T+1] upstream gradient  ->  guref dev [B][2][T],  gxref0 dev [B][5] or NULL
+ */
+int dp_xref_traj(const float *xref0, int xref0_batched, const float *uref, float dt, int B, int T, float *xref,
+                 void *stream);
+int dp_xref_traj_bwd(const float *xref, const float *gxref, float dt, int B, int T, float *guref, float *gxref0,
+                     void *stream);
+
+/*
+ * Goal and state-bounds terms of MotionPlanner.get_cost:
+ *   get_cost_goal   motion_planning/MotionPlanner.py:121-147   sum_s rho[s,-1] * |x[s,:2,-1] - goal|^2      (or max)
+ *   get_cost_bounds motion_planning/MotionPlanner.py:149-190   sum over (s, d, t) with x < lo_d of rho (x - lo_d)^2, the
+ *                   same above hi_d (or the max of each part)
+ *   x dev: element (n, d, t) at x[n*sx_n + d*sx_d + t*sx_t], d = 0..4;  rho dev (n, t) at rho[n*sr_n + t*sr_t]
+ *   lo5, hi5, goal_xy: HOST float[5], [5], [2]
+ *   out3 dev double[3] = {goal, below-bound part, above-bound part};  flags2 dev int[2] = {any x < lo, any x > hi} over
+ *   the first four state dimensions (the reference enters a part only then, :173,:181; in_bounds = neither flag)
+ * dp_cost_state_bwd writes (sum mode) gx(n,d,t) and grho(n,t) = s_goal * d goal + s_lo * d below + s_hi * d above.
+ */
+int dp_cost_state(const float *x, int64_t sx_n, int64_t sx_d, int64_t sx_t, const float *rho, int64_t sr_n, int64_t sr_t,
+                  int64_t N, int Ts, const float *lo5, const float *hi5, const float *goal_xy, int get_max, double *out3,
+                  int *flags2, void *stream);
+int dp_cost_state_bwd(const float *x, int64_t sx_n, int64_t sx_d, int64_t sx_t, const float *rho, int64_t sr_n, int64_t sr_t,
+                      int64_t N, int Ts, const float *lo5, const float *hi5, const float *goal_xy, float s_goal, float s_lo,
+                      float s_hi, float *gx, int64_t sg_n, int64_t sg_d, int64_t sg_t, float *grho, int64_t sgr_n,
+                      int64_t sgr_t, void *stream);
+
 /* Diagnostic: one 128 x n x 128 product through the TMEM-operand tcgen05.mma path of the tensor-core rollout
  * (split-precision fp16 operands).  A host fp32 [128][128], W host fp32 [n_valid][128] zero-padded to n rows
  * (n in {128, 48, 32}), mode 0 = value path (3 products), 1 = fp16 activations x (hi + lo) weights (2 products); D host fp32 [128][n]

@@ -288,3 +288,73 @@ def normalize_density(rholog, rho0):
     m = rholog.max(axis=0, keepdims=True)
     un = np.exp(rholog - m) * np.asarray(rho0, _F).reshape(-1, 1)
     return (un / un.sum(axis=0, keepdims=True, dtype=_F)).astype(_F)
+
+
+# ---- reference-trajectory integrator and goal / bounds cost terms ---------------------
+def xref_traj(xref0, uref, dt):
+    """compute_xref_traj (systems/ControlAffineSystem.py:341-354; CAR dynamics sytem_CAR.py:128-176), fp32 op for op.
+    xref0 (B,5) or (5,), uref (B,2,T) -> xref (B,5,T+1)."""
+    uref = np.asarray(uref, np.float32)
+    B, _, T = uref.shape
+    x = np.broadcast_to(np.asarray(xref0, np.float32).reshape(-1, 5), (B, 5)).copy()
+    dt = np.float32(dt)
+    out = np.empty((B, 5, T + 1), np.float32)
+    out[:, :, 0] = x
+    for k in range(T):
+        cs, sn = np.cos(x[:, 2]).astype(np.float32), np.sin(x[:, 2]).astype(np.float32)
+        x = x.copy()
+        x[:, 0] = x[:, 0] + (x[:, 3] * cs) * dt
+        x[:, 1] = x[:, 1] + (x[:, 3] * sn) * dt
+        x[:, 2] = x[:, 2] + uref[:, 0, k] * dt
+        x[:, 3] = x[:, 3] + uref[:, 1, k] * dt
+        out[:, :, k + 1] = x
+    return out
+
+
+def xref_traj_grad(xref, gxref, dt):
+    """Discrete adjoint of xref_traj in float64: upstream gxref (B,5,T+1) -> (guref (B,2,T), gxref0 (B,5))."""
+    xref = np.asarray(xref, np.float64)
+    g = np.asarray(gxref, np.float64)
+    B, _, T1 = xref.shape
+    T = T1 - 1
+    lam = np.zeros((B, 5))
+    gu = np.zeros((B, 2, T))
+    for k in range(T, 0, -1):
+        lam = lam + g[:, :, k]
+        gu[:, 0, k - 1] = lam[:, 2] * dt
+        gu[:, 1, k - 1] = lam[:, 3] * dt
+        th, v = xref[:, 2, k - 1], xref[:, 3, k - 1]
+        cs, sn = np.cos(th), np.sin(th)
+        lth = lam[:, 2] + dt * v * (cs * lam[:, 1] - sn * lam[:, 0])
+        lv = lam[:, 3] + dt * (cs * lam[:, 0] + sn * lam[:, 1])
+        lam = lam.copy()
+        lam[:, 2], lam[:, 3] = lth, lv
+    return gu, lam + g[:, :, 0]
+
+
+def cost_goal_bounds(x, rho, lo, hi, goal_xy, get_max=False, want_grad=False):
+    """Raw terms of get_cost_goal / get_cost_bounds (motion_planning/MotionPlanner.py:121-190): x (N,5,Ts), rho (N,Ts).
+    Returns dict(goal, below, above, any_lo4, any_hi4[, gx, grho for unit upstream factors on all three terms])."""
+    x = np.asarray(x, np.float32)
+    rho = np.asarray(rho, np.float32)
+    lo = np.asarray(lo, np.float32).reshape(1, 5, 1)
+    hi = np.asarray(hi, np.float32).reshape(1, 5, 1)
+    red = (lambda a: float(a.max()) if a.size else 0.0) if get_max else (lambda a: float(a.astype(np.float64).sum()))
+    mlo, mhi = x < lo, x > hi
+    elo = (x - lo).astype(np.float32)
+    ehi = (x - hi).astype(np.float32)
+    r3 = rho[:, None, :]
+    tlo = (r3 * (elo * elo))[mlo]
+    thi = (r3 * (ehi * ehi))[mhi]
+    e = x[:, :2, -1] - np.asarray(goal_xy, np.float32)[None]
+    sq = (e[:, 0] * e[:, 0] + e[:, 1] * e[:, 1]).astype(np.float32)
+    out = dict(goal=red(rho[:, -1] * sq), below=red(tlo), above=red(thi), any_lo4=bool(mlo[:, :4].any()),
+               any_hi4=bool(mhi[:, :4].any()))
+    if want_grad:
+        gx = np.zeros(x.shape, np.float64)
+        gx += np.where(mlo, 2.0 * r3 * np.where(mlo, elo, 0), 0.0) + np.where(mhi, 2.0 * r3 * np.where(mhi, ehi, 0), 0.0)
+        gx[:, :2, -1] += 2.0 * rho[:, -1:] * e
+        gr = (np.where(mlo, elo.astype(np.float64) ** 2, 0.0) + np.where(mhi, ehi.astype(np.float64) ** 2, 0.0)).sum(axis=1)
+        gr[:, -1] += sq
+        out.update(gx=gx, grho=gr)
+    return out

@@ -264,6 +264,70 @@ def gen_env(car, args, seeds):
         save("env_seed%d.npz" % seed, **out)
 
 
+def gen_planner_terms(car, args):
+    """the reference-trajectory integrator up2ref_traj (ControlAffineSystem.py:341-379)
+    with its gradient w.r.t. the input parameters, and the goal / bounds cost terms of MotionPlanner.get_cost
+    (MotionPlanner.py:121-190) with their gradients."""
+    rh.install()
+    with rh.ref_cwd():
+        from motion_planning.example_objects import create_mp_task
+        from motion_planning.MotionPlannerGrad import MotionPlannerGrad
+    os.makedirs("/tmp/dp_log", exist_ok=True)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    with rh.ref_cwd():
+        ego = create_mp_task(args, 0)
+        planner = MotionPlannerGrad(ego, path_log="/tmp/dp_log/")
+    out = {}
+    # (1) integrator: 6 parameter sets through the planner's own call (xref0 repeated per trajectory)
+    g = torch.Generator().manual_seed(31)
+    up = (1.5 * torch.randn(6, 2, 10, generator=g)).requires_grad_(True)
+    xref0 = ego.xref0.repeat(6, 1, 1)
+    uref_l, xref_l = car.up2ref_traj(xref0, up, args, short=False)
+    w = torch.randn(xref_l.shape, generator=g)
+    loss = (w * xref_l).sum() + 0.1 * (uref_l ** 2).sum()
+    loss.backward()
+    uref_s, xref_s = car.up2ref_traj(xref0, up.detach(), args, short=True)
+    out.update(int_up=up.detach(), int_xref0=ego.xref0[0, :, 0], int_uref=uref_l.detach(), int_xref=xref_l.detach(),
+               int_w=w, int_gup=up.grad.clone(), int_xref_short=xref_s, int_uref_short=uref_s, int_loss=loss.detach())
+    # (2) goal / bounds costs on a synthetic weighted sample set with excursions beyond the planner's state bounds
+    rs = np.random.RandomState(41)
+    N, Ts = 3000, 101
+    x = np.zeros((N, 5, Ts), np.float32)
+    tt = np.linspace(0, 1, Ts, dtype=np.float32)
+    x[:, 0, :] = 0.5 * np.sin(3 * tt)[None] + rs.normal(0, 4.0, (N, 1)) * tt[None] + rs.normal(0, 0.2, (N, Ts))
+    x[:, 1, :] = (-28 + 40 * tt)[None] + rs.normal(0, 0.5, (N, Ts))
+    x[:, 2, :] = 1.5 + rs.normal(0, 1.2, (N, Ts))
+    x[:, 3, :] = 5.0 + rs.normal(0, 2.5, (N, Ts))
+    x[:, 4, :] = rs.normal(0, 0.1, (N, 1))
+    rho = rs.uniform(0, 1, (N, 1, Ts)).astype(np.float32)
+    rho /= rho.sum(axis=0, keepdims=True)
+    out.update(cost_x=x, cost_rho=rho[:, 0, :], xrefN=ego.xrefN[0, :, 0], x_min=car.X_MIN[0, :, 0], x_max=car.X_MAX[0, :, 0],
+               x_min_mp=car.X_MIN_MP[0, :, 0], x_max_mp=car.X_MAX_MP[0, :, 0],
+               close2goal_thr=np.float32(args.close2goal_thr), weight_goal_far=np.float32(args.weight_goal_far))
+    for evaluate in (False, True):
+        for get_max in (False, True):
+            xt = torch.from_numpy(x).clone().requires_grad_(True)
+            rt = torch.from_numpy(rho).clone().requires_grad_(True)
+            tag = "e%d_m%d" % (int(evaluate), int(get_max))
+            if get_max:  # evaluation-only variant (the reference's in-place re-weighting of a max output has no backward)
+                with torch.no_grad():
+                    cg, close = planner.get_cost_goal(xt, rt, evaluate=evaluate, get_max=True)
+                    cb, inb = planner.get_cost_bounds(xt, rt, evaluate=evaluate, get_max=True)
+            else:
+                cg, close = planner.get_cost_goal(xt, rt, evaluate=evaluate, get_max=False)
+                cb, inb = planner.get_cost_bounds(xt, rt, evaluate=evaluate, get_max=False)
+                (cg.sum() + cb.sum()).backward()
+                out.update({"gx_" + tag: xt.grad.clone(), "grho_" + tag: rt.grad[:, 0, :].clone()})
+            out.update({"goal_" + tag: cg.detach(), "close_" + tag: np.array(bool(close)), "bounds_" + tag: cb.detach(),
+                        "inb_" + tag: np.array(bool(inb))})
+    # all samples inside the bounds: zero cost, in_bounds True
+    xin = np.clip(x, car.X_MIN_MP[0, :, 0].numpy()[None, :, None] + 0.5, np.minimum(car.X_MAX_MP[0, :, 0].numpy(), 1e6)[None, :, None] - 0.5)
+    cb, inb = planner.get_cost_bounds(torch.from_numpy(xin), torch.from_numpy(rho))
+    out.update(bounds_inside=cb, inb_inside=np.array(bool(inb)))
+    save("planner_terms.npz", **out)
+
+
 def gen_data(car, args):
     """compute_data (data_generation/compute_rawdata.py:9) with a fixed seed: RNG-order golden (config 1)."""
     rh.install()
@@ -280,7 +344,7 @@ def gen_data(car, args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="weights,rollout,step,grid,env,data")
+    ap.add_argument("--only", default="weights,rollout,step,grid,env,data,planner")
     ap.add_argument("--env-seeds", default="0,1,2,3,4,5,6,7,8,9")
     a = ap.parse_args()
     which = a.only.split(",")
@@ -298,6 +362,8 @@ def main():
         gen_data(car, args)
     if "env" in which:
         gen_env(car, args, [int(s) for s in a.env_seeds.split(",")])
+    if "planner" in which:
+        gen_planner_terms(car, args)
     print("done in %.1f s" % (time.time() - t0))
 
 

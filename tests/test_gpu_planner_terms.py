@@ -1,0 +1,82 @@
+"""GPU parity tests of the planner-side terms: the reference-trajectory integrator with
+its analytic backward, and the goal / bounds cost terms, against goldens minted from the unmodified reference and against
+the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_integrator_forward_and_gradient(car, oracle, args):
+    g = golden("planner_terms.npz")
+    up = torch.from_numpy(g["int_up"]).cuda().requires_grad_(True)
+    xref0 = torch.from_numpy(g["int_xref0"]).reshape(1, 5, 1).repeat(6, 1, 1).cuda()
+    uref, xref = car.up2ref_traj(xref0, up, args, short=False)
+    assert xref.is_cuda and xref.shape == (6, 5, 1001) and uref.shape == (6, 2, 999 + 0) or uref.shape == (6, 2, 1000)
+    assert np.abs(xref.detach().cpu().numpy() - g["int_xref"]).max() < 2e-4
+    w = torch.from_numpy(g["int_w"]).cuda()
+    loss = (w * xref).sum() + 0.1 * (uref ** 2).sum()
+    loss.backward()
+    assert abs(float(loss) - float(g["int_loss"])) < 1e-4 * abs(float(g["int_loss"]))
+    assert np.abs(up.grad.cpu().numpy() - g["int_gup"]).max() < 2e-4 * np.abs(g["int_gup"]).max()
+    us, xs = car.up2ref_traj(xref0, up.detach(), args, short=True)
+    assert np.abs(xs.cpu().numpy() - g["int_xref_short"]).max() < 2e-4 and (us.cpu().numpy() == g["int_uref_short"]).all()
+    # shared start state (batch dimension 1) and its gradient
+    x0 = torch.from_numpy(g["int_xref0"]).reshape(1, 5, 1).cuda().requires_grad_(True)
+    u = torch.from_numpy(g["int_uref"]).cuda()
+    xr = car.compute_xref_traj(x0, u, args)
+    (w[:, :, :xr.shape[2]] * xr).sum().backward()
+    _, gx0 = oracle.xref_traj_grad(g["int_xref"][:, :, :xr.shape[2]], g["int_w"][:, :, :xr.shape[2]], 0.01)
+    assert np.abs(x0.grad[0, :, 0].cpu().numpy() - gx0.sum(axis=0)).max() < 2e-4 * np.abs(gx0.sum(axis=0)).max()
+
+
+def test_reference_integrator_vs_oracle_batch(car, oracle, args):
+    """100 trajectories (the planner's initialisation batch), bit-level agreement of the op order with the oracle."""
+    rs = np.random.RandomState(5)
+    B, T = 100, 1000
+    uref = rs.uniform(-3, 3, (B, 2, T)).astype(np.float32)
+    x0 = np.array([0.0, -25.0, 1.5, 3.0, 0.0], np.float32)
+    got = car.compute_xref_traj(torch.from_numpy(x0).reshape(1, 5, 1).cuda(), torch.from_numpy(uref).cuda(), args)
+    ref = oracle.xref_traj(x0, uref[:, :, :got.shape[2] - 1], 0.01)
+    assert np.abs(got.cpu().numpy() - ref).max() < 5e-4
+
+
+@pytest.mark.parametrize("ev", [0, 1])
+@pytest.mark.parametrize("mx", [0, 1])
+def test_goal_and_bounds_costs_vs_reference_golden(dp, car, args, ev, mx):
+    g = golden("planner_terms.npz")
+    tag = "e%d_m%d" % (ev, mx)
+    x = torch.from_numpy(g["cost_x"]).cuda().requires_grad_(not mx)
+    rho = torch.from_numpy(g["cost_rho"]).unsqueeze(1).cuda().requires_grad_(not mx)
+    xrefN = torch.from_numpy(g["xrefN"]).reshape(1, 5, 1)
+    cg, close = dp.get_cost_goal(x, rho, xrefN, args, evaluate=bool(ev), get_max=bool(mx))
+    cb, inb = dp.get_cost_bounds(x, rho, car, evaluate=bool(ev), get_max=bool(mx))
+    assert bool(close) == bool(g["close_" + tag]) and bool(inb) == bool(g["inb_" + tag])
+    assert abs(float(cg) - float(g["goal_" + tag])) <= 1e-4 * abs(float(g["goal_" + tag]))
+    assert cb.shape == (1,) and abs(float(cb) - float(g["bounds_" + tag][0])) <= 1e-4 * abs(float(g["bounds_" + tag][0]))
+    if not mx:
+        (cg.sum() + cb.sum()).backward()
+        gx, gr = x.grad.cpu().numpy(), rho.grad[:, 0, :].cpu().numpy()
+        assert np.abs(gx - g["gx_" + tag]).max() <= 1e-5 * np.abs(g["gx_" + tag]).max()
+        assert np.abs(gr - g["grho_" + tag]).max() <= 1e-5 * np.abs(g["grho_" + tag]).max()
+
+
+def test_bounds_cost_inside_and_native_layout(dp, car, args):
+    g = golden("planner_terms.npz")
+    x = torch.from_numpy(g["cost_x"]).cuda()
+    rho = torch.from_numpy(g["cost_rho"]).unsqueeze(1).cuda()
+    lo = car.X_MIN_MP[0, :, 0].numpy()
+    hi = np.minimum(car.X_MAX_MP[0, :, 0].numpy(), 1e6)
+    xin = torch.minimum(torch.maximum(x, torch.from_numpy(lo + 0.5).cuda().reshape(1, 5, 1)),
+                        torch.from_numpy(hi - 0.5).cuda().reshape(1, 5, 1))
+    cb, inb = dp.get_cost_bounds(xin, rho, car)
+    assert float(cb) == 0.0 and bool(inb)
+    # the kernel-native [t][d][n] storage (a permuted view) gives the same numbers as the reference layout
+    xt = x.permute(2, 1, 0).contiguous().permute(2, 1, 0)
+    rt = rho.permute(2, 1, 0).contiguous().permute(2, 1, 0)
+    a, _ = dp.get_cost_bounds(x, rho, car)
+    b, _ = dp.get_cost_bounds(xt, rt, car)
+    assert abs(float(a) - float(b)) <= 1e-12 * abs(float(a))

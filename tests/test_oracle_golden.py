@@ -155,3 +155,48 @@ def test_normalizer_matches_reference_planner_call(oracle, blob):
     big = ref > 1e-6
     assert np.abs(rho[big] / ref[big] - 1).max() < 5e-3
     assert np.abs(rho.sum(axis=0) - 1).max() < 1e-4
+
+
+def test_oracle_reference_integrator_vs_golden(oracle):
+    """compute_xref_traj / up2ref_traj and its gradient w.r.t. the input parameters."""
+    g = golden("planner_terms.npz")
+    xref = oracle.xref_traj(g["int_xref0"], g["int_uref"], 0.01)
+    assert xref.shape == g["int_xref"].shape
+    assert np.abs(xref - g["int_xref"]).max() < 2e-4  # torch's and numpy's cos/sin differ in the last bit over 1000 steps
+    assert np.abs(xref[:, :, ::10] - g["int_xref_short"]).max() < 2e-4
+    # loss = sum(w * xref) + 0.1 * sum(uref^2); uref = repeat_interleave(up, 100)[:, :, :999]
+    gu, _ = oracle.xref_traj_grad(g["int_xref"], g["int_w"], 0.01)
+    gu = gu + 0.2 * g["int_uref"]
+    gup = np.zeros((6, 2, 10))
+    for k in range(gu.shape[2]):
+        gup[:, :, k // 100] += gu[:, :, k]
+    assert np.abs(gup - g["int_gup"]).max() < 2e-4 * np.abs(g["int_gup"]).max()
+
+
+def test_oracle_goal_bounds_costs_vs_golden(oracle):
+    """get_cost_goal / get_cost_bounds forward (sum and max) and gradients."""
+    g = golden("planner_terms.npz")
+    for ev in (0, 1):
+        lo, hi = (g["x_min"], g["x_max"]) if ev else (g["x_min_mp"], g["x_max_mp"])
+        for mx in (0, 1):
+            tag = "e%d_m%d" % (ev, mx)
+            o = oracle.cost_goal_bounds(g["cost_x"], g["cost_rho"], lo, hi, g["xrefN"][:2], get_max=bool(mx), want_grad=not mx)
+            goal = o["goal"]
+            close = goal < float(g["close2goal_thr"])
+            assert close == bool(g["close_" + tag])
+            if not ev and not close:
+                goal *= float(g["weight_goal_far"])
+            assert abs(goal - float(g["goal_" + tag])) <= 2e-5 * abs(float(g["goal_" + tag]))
+            bounds = o["below"] * o["any_lo4"] + o["above"] * o["any_hi4"]
+            assert abs(bounds - float(g["bounds_" + tag][0])) <= 2e-5 * abs(float(g["bounds_" + tag][0]))
+            assert (not (o["any_lo4"] or o["any_hi4"])) == bool(g["inb_" + tag])
+            if not mx:
+                s_goal = 1.0 if (ev or close) else float(g["weight_goal_far"])
+                gx = o["gx"].copy()
+                gx[:, :2, -1] *= 1.0  # goal part already has unit factor; rescale below
+                e = g["cost_x"][:, :2, -1] - g["xrefN"][None, :2]
+                gx[:, :2, -1] += (s_goal - 1.0) * 2.0 * g["cost_rho"][:, -1:] * e
+                gr = o["grho"].copy()
+                gr[:, -1] += (s_goal - 1.0) * (e ** 2).sum(axis=1)
+                assert np.abs(gx - g["gx_" + tag]).max() <= 1e-5 * np.abs(g["gx_" + tag]).max()
+                assert np.abs(gr - g["grho_" + tag]).max() <= 1e-5 * np.abs(g["grho_" + tag]).max()
