@@ -80,3 +80,39 @@ def test_bounds_cost_inside_and_native_layout(dp, car, args):
     a, _ = dp.get_cost_bounds(x, rho, car)
     b, _ = dp.get_cost_bounds(xt, rt, car)
     assert abs(float(a) - float(b)) <= 1e-12 * abs(float(a))
+
+
+def test_attach_binds_the_kernel_backed_calls(dp, oracle, args):
+    """`dp.attach(planner)` on a stand-in for the reference's planner / ego objects (same attribute names): every bound
+    call returns what the reference returned for the same inputs (goldens of env seed 0 and the planner terms)."""
+    import types
+    e = golden("env_seed0.npz")
+    pt = golden("planner_terms.npz")
+    gx, gy = oracle.env_gradient(e["grid"])
+    env = types.SimpleNamespace(grid=torch.from_numpy(e["grid"]), grid_gradientX=torch.from_numpy(gx),
+                                grid_gradientY=torch.from_numpy(gy))
+    ref_system = types.SimpleNamespace()  # the reference's Car; only up2ref_traj is (re)bound on it
+    ego = types.SimpleNamespace(env=env, args=args, system=ref_system,
+                                xref0=torch.from_numpy(e["le_xref0"]).reshape(1, 5, 1),
+                                xe0=torch.from_numpy(e["le_xe0"]).unsqueeze(-1),
+                                rho0=torch.from_numpy(e["le_rho0"]).reshape(-1, 1, 1),
+                                xrefN=torch.from_numpy(pt["xrefN"]).reshape(1, 5, 1),
+                                predict_density=lambda *a, **k: (_ for _ in ()).throw(AssertionError("NN branch called")))
+    planner = types.SimpleNamespace(ego=ego, get_cost_coll=None, get_cost_goal=lambda *a, **k: None, get_cost_bounds=None,
+                                    get_cost_coll_initialize=lambda x: (_ for _ in ()).throw(AssertionError("reference init")))
+    dp.attach(planner)
+    up = torch.from_numpy(e["le_up"])
+    uref_traj, xref_traj = ego.system.up2ref_traj(ego.xref0, up, args, short=True)
+    assert uref_traj.device.type == "cpu" and xref_traj.shape == (1, 5, 101)
+    x_traj, rho_traj = ego.predict_density(up, xref_traj, use_nn=False)
+    assert np.abs(x_traj[:, :2, :].numpy() - e["le_x"]).max() < 2e-4
+    c = planner.get_cost_coll(x_traj, rho_traj)
+    assert abs(float(c) - e["le_cost"][0]) <= 2e-3 * abs(e["le_cost"][0])
+    ci = planner.get_cost_coll_initialize(x_traj[:100])
+    assert np.abs(ci.numpy() - e["le_cost_init"]).max() <= 1e-4 * np.abs(e["le_cost_init"]).max()
+    xs = torch.from_numpy(pt["cost_x"])
+    rs = torch.from_numpy(pt["cost_rho"]).unsqueeze(1)
+    cg, close = planner.get_cost_goal(xs, rs, evaluate=False, get_max=False)
+    cb, inb = planner.get_cost_bounds(xs, rs, evaluate=False, get_max=False)
+    assert cg.device.type == "cpu" and abs(float(cg) - float(pt["goal_e0_m0"])) <= 1e-4 * float(pt["goal_e0_m0"])
+    assert abs(float(cb) - float(pt["bounds_e0_m0"][0])) <= 1e-4 * float(pt["bounds_e0_m0"][0]) and not bool(inb)
