@@ -409,6 +409,45 @@ def main():
                           "frac_of_hbm_peak": ev * nbytes / 1e9 / cfg3["hbm_peak_gbs"]}
         del x3, y3, r3, gx3, gy3, gr3, m3, n3
 
+    # ---- BASELINE config 1 shape: 20 samples x 1000 steps per reference (data_generation/compute_rawdata.py): one
+    #      reference per launch (the reference's call pattern) and 296 references in one launch (dp_rollout_batch) --------
+    cfg1 = None
+    if rank == 0:
+        n1, T1c, R1 = 20, 1000, 2 * 148
+        torch.manual_seed(7)
+        refs = []
+        while len(refs) < 8:
+            _, u1, x1 = car.get_valid_ref(args)
+            if u1.shape[2] >= T1c:
+                refs.append((u1[0, :, :T1c], x1[0, :, :T1c + 1]))
+        ur1 = torch.stack([refs[r % 8][0] for r in range(R1)]).contiguous().to(dev)
+        xr1 = torch.stack([refs[r % 8][1] for r in range(R1)]).contiguous().to(dev)
+        xe1 = car.sample_xe0(R1 * n1).reshape(R1 * n1, 5).to(dev)
+        xo1 = torch.empty((T1c + 1, 5, R1 * n1), dtype=torch.float32, device=dev)
+        lo1 = torch.empty((T1c + 1, R1 * n1), dtype=torch.float32, device=dev)
+        h = car.controller.controller.handle
+
+        def one_ref():
+            _lib.check(L.dp_rollout(h, _lib.ptr(xe1), _lib.ptr(xr1), _lib.ptr(ur1), None, float(args.dt_sim), n1, T1c, flags, 1,
+                                    _lib.ptr(xo1), _lib.ptr(lo1), R1 * n1, None, None, sp), "dp_rollout")
+
+        def all_refs():
+            _lib.check(L.dp_rollout_batch(h, _lib.ptr(xe1), _lib.ptr(xr1), _lib.ptr(ur1), None, None, float(args.dt_sim), R1, n1,
+                                          T1c, flags, 1, _lib.ptr(xo1), _lib.ptr(lo1), R1 * n1, None, None, sp), "dp_rollout_batch")
+
+        cfg1 = {"workload": "%d samples x %d steps per reference, every step stored (BASELINE config 1 shape)" % (n1, T1c)}
+        for name, fn, work in (("one_reference_per_launch", one_ref, n1 * T1c), ("batched_%d_references" % R1, all_refs, R1 * n1 * T1c)):
+            fn()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(3):
+                fn()
+            a1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms = a0.elapsed_time(a1) / 3
+            cfg1[name] = {"ms": ms, "sample_steps_per_s": work / (ms * 1e-3)}
+        del xo1, lo1
+
     if rank != 0:
         return
     peaks, peaks_src = measured_peaks()
@@ -442,7 +481,7 @@ def main():
                        "parallelism": "samples sharded, %d rank(s); allreduce of normaliser stats, cost and int grids" % world},
             "e2e": e2e, "gpu_launches": launches["n"], "clocks": clk, "roofline": roofline,
             "collision_cost_evals_per_s": cfg3["cost_fwd"]["evals_per_s"] if cfg3 else cost_evals * world,
-            "collision_cost_config3": cfg3,
+            "collision_cost_config3": cfg3, "rawdata_config1": cfg1,
             "checks": {"grid_count_total": total_count, "grid_mass_total": total_mass, "cost_total": cost_total,
                        "occupancy_dot_total": float(occ_dot.sum().item())}}
     if not opts.no_cpu_baseline and world == 1:

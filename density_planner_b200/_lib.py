@@ -40,6 +40,7 @@ _SIGNATURES = {
     "dp_controller_create": (_int, [_vp, ctypes.c_size_t, _int, ctypes.POINTER(_vp)]),
     "dp_controller_destroy": (None, [_vp]),
     "dp_rollout": (_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _int, _uint, _int, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "dp_rollout_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i64, _int, _uint, _int, _vp, _vp, _i64, _vp, _vp, _vp]),
     "dp_rollout_host": (_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _int, _uint, _int, _vp, _vp, _vp, _vp]),
     "dp_step": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dp_pos2gridpos": (_int, [ctypes.POINTER(GridGeom), _vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),

@@ -102,13 +102,33 @@ int dp_rollout(const dp_controller *c, const float *xe0, const float *xref, cons
     p.big = c->d_big; p.small = c->d_small; p.tc = c->d_tc;
     p.xe0 = xe0; p.xref = xref; p.uref = uref; p.rho0 = rho0;
     p.dt = dt; p.N = N; p.T = T; p.flags = flags; p.stride = stride; p.Ts = T / stride + 1;
-    p.x_out = x_out; p.rho_out = rho_out; p.ldn = ldn; p.clip_margin = clip_margin; p.status = status; p.trace = nullptr;
+    p.x_out = x_out; p.rho_out = rho_out; p.ldn = ldn; p.clip_margin = clip_margin; p.status = status; p.trace = nullptr; p.R = 1; p.n_per_ref = N; p.T_ref = nullptr;
     const unsigned impl = flags & DP_IMPL_MASK;
     // default = the tcgen05 kernel (fp32-level value path); DP_IMPL_FFMA selects the all-fp32 CUDA-core kernel
     if (impl == DP_IMPL_TC || impl == DP_IMPL_DEFAULT) return dp_launch_rollout_tc(c, p, (cudaStream_t)stream);
     if (impl == DP_IMPL_FFMA) return dp_launch_rollout_ffma(c, p, (cudaStream_t)stream);
     dp_set_error("dp_rollout: unknown implementation selector 0x%x", impl);
     return 2;
+}
+
+int dp_rollout_batch(const dp_controller *c, const float *xe0, const float *xref, const float *uref, const int *T_ref,
+                     const float *rho0, float dt, int64_t R, int64_t n_per_ref, int T, unsigned flags, int stride, float *x_out,
+                     float *rho_out, int64_t ldn, float *clip_margin, int *status, void *stream) {
+    DP_REQUIRE(c && xe0 && xref && uref, "dp_rollout_batch: null argument");
+    DP_REQUIRE(T >= 0 && stride >= 1 && R >= 0 && n_per_ref >= 0, "dp_rollout_batch: bad sizes");
+    const int64_t N = R * n_per_ref;
+    DP_REQUIRE(ldn >= N || (!x_out && !rho_out), "dp_rollout_batch: ldn=%lld < N=%lld", (long long)ldn, (long long)N);
+    const unsigned impl = flags & DP_IMPL_MASK;
+    DP_REQUIRE(impl == DP_IMPL_TC || impl == DP_IMPL_DEFAULT, "dp_rollout_batch: only the tensor-core kernel takes several references");
+    if (N <= 0) return 0;
+    DeviceGuard guard(c->device);
+    RolloutParams p;
+    p.big = c->d_big; p.small = c->d_small; p.tc = c->d_tc;
+    p.xe0 = xe0; p.xref = xref; p.uref = uref; p.rho0 = rho0;
+    p.dt = dt; p.N = N; p.T = T; p.flags = flags; p.stride = stride; p.Ts = T / stride + 1;
+    p.x_out = x_out; p.rho_out = rho_out; p.ldn = ldn; p.clip_margin = clip_margin; p.status = status; p.trace = nullptr;
+    p.R = R; p.n_per_ref = n_per_ref; p.T_ref = T_ref;
+    return dp_launch_rollout_tc(c, p, (cudaStream_t)stream);
 }
 
 static int ws_reserve(dp_controller *c, size_t bytes) {
@@ -130,10 +150,11 @@ int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const
     DeviceGuard guard(c->device);
     const int Ts = T / stride + 1;
     const int nd = (flags & DP_XY_ONLY) ? 2 : 5;
-    // Samples are processed in chunks of whole waves (128 samples x #SMs x 8); the device->host copy of chunk k overlaps
-    // the rollout of chunk k+1 (two output buffers, a compute stream and a copy stream).
-    const int64_t wave = 128LL * c->num_sms;
-    int64_t chunk = 8 * wave;
+    // Samples are processed in chunks of two whole waves (one wave = 2 tiles of 128 samples per SM); the device->host copy
+    // of chunk k overlaps the rollout of chunk k+1 (two output buffers, a compute stream and a copy stream).  Small chunks
+    // keep the exposed tail (the last chunk's copy) short: ~13 chunks for 1M samples.
+    const int64_t wave = 2 * 128LL * c->num_sms;
+    int64_t chunk = 2 * wave;
     if (chunk > N) chunk = N;
     const int64_t nchunks = (N + chunk - 1) / chunk;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };

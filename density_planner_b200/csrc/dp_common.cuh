@@ -105,6 +105,10 @@ struct RolloutParams {
     float *clip_margin;
     int *status;
     unsigned long long *trace;  // optional in-kernel timeline (DP_TC_TRACE), normally null
+    // several references in one launch (dp_rollout_batch): xref [R][5][T+1], uref [R][2][T], n_per_ref samples each,
+    // optional per-reference horizons T_ref[R] <= T (device); R <= 1: one shared reference
+    long long R, n_per_ref;
+    const int *T_ref;
 };
 
 int dp_launch_rollout_ffma(const dp_controller *c, const RolloutParams &p, cudaStream_t stream);

@@ -509,7 +509,7 @@ __device__ __forceinline__ void sample_advance(const RolloutParams &p, SampleSta
     st.x3 = __fadd_rn(st.x3, __fmul_rn(u1, dt));
 }
 
-template <int TP, int TOKEN, int KC>
+template <int TP, int TOKEN, int KC, int BATCH>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -557,11 +557,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
     float *sPart = reinterpret_cast<float *>(smem + OFF_PART) + grp * 2 * 4 * TILE;
     uint32_t ph = 0;
 
-    const int T = p.T, T1 = p.T + 1;
+    const int T1 = p.T + 1;
     const bool logd = p.flags & DP_LOG_DENSITY, dens = p.flags & DP_DENSITY, cut = p.flags & DP_CUT;
     const bool abs_state = p.flags & DP_ABS_STATE;
     const int nd = (p.flags & DP_XY_ONLY) ? 2 : 5;
-    const long long num_tiles = (p.N + TILE - 1) / TILE;
+    const long long num_tiles = BATCH ? p.R * ((p.n_per_ref + TILE - 1) / TILE) : (p.N + TILE - 1) / TILE;
 
     // both groups run the same number of chains (a group without a tile in the last round runs a dummy one: the token
     // hand-off is symmetric)
@@ -581,25 +581,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
     const long long num_rounds = (num_tiles + NGROUPS - 1) / NGROUPS;
     for (long long round = blockIdx.x; round < num_rounds; round += gridDim.x) {
         const long long tile = round * NGROUPS + grp;
-        const long long n = tile * TILE + c.s;
-        const bool valid = n < p.N;
+        // sample of this thread; with several references (dp_rollout_batch) a tile belongs to exactly one of them
+        long long n, ref = 0;
+        bool valid;
+        if (BATCH) {
+            const long long tiles_per_ref = (p.n_per_ref + TILE - 1) / TILE;
+            ref = tile / tiles_per_ref;
+            const long long k = (tile - ref * tiles_per_ref) * TILE + c.s;
+            valid = ref < p.R && k < p.n_per_ref;
+            if (ref >= p.R) ref = p.R - 1;
+            n = ref * p.n_per_ref + k;
+        } else {
+            n = tile * TILE + c.s;
+            valid = n < p.N;
+        }
         const long long nl = valid ? n : p.N - 1;
+        const float *xref = BATCH ? p.xref + ref * 5 * T1 : p.xref, *uref = BATCH ? p.uref + ref * 2 * p.T : p.uref;
+        const int T = (BATCH && p.T_ref) ? __ldg(p.T_ref + ref) : p.T;  // this reference's horizon (rows are padded to p.T)
         SampleState st;
-        st.x0 = __ldg(p.xe0 + nl * 5 + 0) + __ldg(p.xref + 0 * T1);
-        st.x1 = __ldg(p.xe0 + nl * 5 + 1) + __ldg(p.xref + 1 * T1);
-        st.x2 = __ldg(p.xe0 + nl * 5 + 2) + __ldg(p.xref + 2 * T1);
-        st.x3 = __ldg(p.xe0 + nl * 5 + 3) + __ldg(p.xref + 3 * T1);
-        st.x4 = __ldg(p.xe0 + nl * 5 + 4) + __ldg(p.xref + 4 * T1);
+        st.x0 = __ldg(p.xe0 + nl * 5 + 0) + __ldg(xref + 0 * T1);
+        st.x1 = __ldg(p.xe0 + nl * 5 + 1) + __ldg(xref + 1 * T1);
+        st.x2 = __ldg(p.xe0 + nl * 5 + 2) + __ldg(xref + 2 * T1);
+        st.x3 = __ldg(p.xe0 + nl * 5 + 3) + __ldg(xref + 3 * T1);
+        st.x4 = __ldg(p.xe0 + nl * 5 + 4) + __ldg(xref + 4 * T1);
         st.rho = p.rho0 ? __ldg(p.rho0 + nl) : (logd ? 0.0f : 1.0f);
         st.margin = 1e30f;
         int next_store = 0, slot = 0;
         if (T > 0) {
-            *cb_mine = fmaf(cb_w, __ldg(p.xref + 3 * T1), cb_b);
+            *cb_mine = fmaf(cb_w, __ldg(xref + 3 * T1), cb_b);
             group_sync(c.bar_id);
         }
         for (int i = 0;; ++i) {
-            const float xr0 = __ldg(p.xref + 0 * T1 + i), xr1 = __ldg(p.xref + 1 * T1 + i);
-            const float xr2 = __ldg(p.xref + 2 * T1 + i), xr3 = __ldg(p.xref + 3 * T1 + i);
+            const float xr0 = __ldg(xref + 0 * T1 + i), xr1 = __ldg(xref + 1 * T1 + i);
+            const float xr2 = __ldg(xref + 2 * T1 + i), xr3 = __ldg(xref + 3 * T1 + i);
             if (i == next_store) {
                 // stored slice: the owner thread (h == 0) of each sample writes; a warp covers 32 consecutive samples per row
                 if (h == 0) {
@@ -627,7 +641,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
                                 if (nd == 5) {
                                     o[2 * p.ldn] = st.x2 - xr2;
                                     o[3 * p.ldn] = st.x3 - xr3;
-                                    o[4 * p.ldn] = st.x4 - __ldg(p.xref + 4 * T1 + i);
+                                    o[4 * p.ldn] = st.x4 - __ldg(xref + 4 * T1 + i);
                                 }
                             }
                         }
@@ -643,7 +657,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
             const float e2 = __fadd_rn(__fsub_rn(st.x2, xr2), st.x4);
             const float4 in = make_float4(st.x2, st.x3, st.x2 - e2, st.x3 - e3);
             const float4 xe = make_float4(e0, e1, e2, e3);
-            const float ur0 = __ldg(p.uref + i), ur1 = __ldg(p.uref + T + i);
+            const float ur0 = __ldg(uref + i), ur1 = __ldg(uref + p.T + i);
 
             float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 1
@@ -655,7 +669,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
             // exchange the partial head sums of the two feature halves (fixed order: both threads get identical totals)
             float *mine = sPart + h * 4 * TILE + c.s;
             mine[0 * TILE] = acc[0]; mine[1 * TILE] = acc[1]; mine[2 * TILE] = acc[2]; mine[3 * TILE] = acc[3];
-            if (i + 1 < T) *cb_mine = fmaf(cb_w, __ldg(p.xref + 3 * T1 + i + 1), cb_b);  // every thread is past both L1 stages
+            if (i + 1 < T) *cb_mine = fmaf(cb_w, __ldg(xref + 3 * T1 + i + 1), cb_b);  // every thread is past both L1 stages
             fence_before();
             group_sync(c.bar_id);
             const float *p0 = sPart + c.s, *p1 = sPart + 4 * TILE + c.s;
@@ -728,9 +742,10 @@ int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStr
     static bool attr_set[64] = {};
     static int variant = -1;  // tuning / A-B knob: DP_TC_VARIANT = 100 * k_chunked + 10 * tangent_products + token
     typedef void (*kern_t)(RolloutParams);
-    static const kern_t kerns[8] = {rollout_tc_kernel<1, 0, 0>, rollout_tc_kernel<1, 1, 0>, rollout_tc_kernel<2, 0, 0>,
-                                    rollout_tc_kernel<2, 1, 0>, rollout_tc_kernel<1, 0, 1>, rollout_tc_kernel<1, 0, 2>,
-                                    rollout_tc_kernel<2, 0, 1>, rollout_tc_kernel<2, 0, 2>};
+    static const kern_t kerns[8] = {rollout_tc_kernel<1, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0>, rollout_tc_kernel<2, 0, 0, 0>,
+                                    rollout_tc_kernel<2, 1, 0, 0>, rollout_tc_kernel<1, 0, 1, 0>, rollout_tc_kernel<1, 0, 2, 0>,
+                                    rollout_tc_kernel<2, 0, 1, 0>, rollout_tc_kernel<2, 0, 2, 0>};
+    static const kern_t kern_batch = rollout_tc_kernel<1, 0, 1, 1>;  // several references per launch (dp_rollout_batch)
     if (variant < 0) {
         const char *e = getenv("DP_TC_VARIANT");
         const int v = e ? atoi(e) : 110;  // 100 * K-chunking (0 off, 1 four batches, 2 two batches) + 10 * tangent products + token
@@ -740,12 +755,14 @@ int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStr
     if (!attr_set[c->device & 63]) {
         for (int k = 0; k < 8; ++k)
             DP_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        DP_CUDA(cudaFuncSetAttribute(kern_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_set[c->device & 63] = true;
     }
-    const kern_t kern = kerns[variant];
+    const bool batch = p.R > 1 || p.T_ref != nullptr;
+    const kern_t kern = batch ? kern_batch : kerns[variant];
     RolloutParams q = p;
     q.tc = c->d_tc;
-    const long long num_tiles = (p.N + TILE - 1) / TILE;
+    const long long num_tiles = (p.R > 1 || p.T_ref) ? p.R * ((p.n_per_ref + TILE - 1) / TILE) : (p.N + TILE - 1) / TILE;
     const long long want = (num_tiles + NGROUPS - 1) / NGROUPS;
     const int grid = (int)(want < c->num_sms ? want : c->num_sms);
     const char *trace_path = getenv("DP_TC_TRACE");  // diagnostic: dump an in-kernel clock64 timeline of CTA 0

@@ -42,3 +42,48 @@ def compute_data(iteration_number, samples_x, system, args, samples_t=None, save
                 pickle.dump([results_all, args], f)
             results_all = []
     return results_all
+
+
+def compute_data_batched(iteration_number, samples_x, system, args, samples_t=None, save=True):
+    """`compute_data` with ONE rollout launch per file instead of one per trajectory.
+
+    The torch RNG is consumed in exactly the reference's order -- per trajectory: reference rejection sampling, initial
+    errors, time-index draw (compute_rawdata.py:26-36; the rollout itself consumes none and the number of time points
+    follows from the reference alone) -- so the result equals `compute_data`'s for the same seed."""
+    results_all = []
+    k = args.factor_pred
+    for _ in range(iteration_number[0]):
+        pending = []
+        for _ in range(iteration_number[1]):
+            up, uref_traj, xref_traj = system.get_valid_ref(args)
+            xe0 = system.sample_xe0(samples_x)
+            t = (args.dt_sim * torch.arange(0, xref_traj.shape[2]))[::k]
+            if samples_t == 0:
+                indizes = args.N_sim - 1
+            elif samples_t is not None:
+                indizes = torch.randint(0, t.shape[0], (int(samples_t),))
+                indizes = list(set(indizes.tolist()))
+            else:
+                indizes = torch.arange(0, t.shape[0])
+            pending.append((up, uref_traj, xref_traj, xe0, t, indizes))
+        outs = system.compute_density_batch([p[3] for p in pending], [p[2] for p in pending], [p[1] for p in pending],
+                                            args.dt_sim, cutting=True, log_density=True, compute_density=True)
+        for (up, uref_traj, xref_traj, xe0, t, indizes), (xe_traj, rho_traj) in zip(pending, outs):
+            xe_s, rho_s = xe_traj[:, :, ::k], rho_traj[:, :, ::k]
+            results_all.append({
+                'u_params': up,
+                'xe0': xe_s[:, :, 0],
+                't': t[indizes],
+                'xref0': xref_traj[0, :, 0],
+                'xe_traj': xe_s[:, :, indizes],
+                'rholog_traj': rho_s[:, :, indizes],
+            })
+        if save:
+            data_name = args.path_rawdata + datetime.now().strftime("%Y-%m-%d-%H-%M-%S") + "_rawData_" + \
+                system.systemname + "_%s_Nsim%d_iter%d_xSamples%d_tSamples%d" % (
+                    args.input_type, args.N_sim, iteration_number[1], samples_x, samples_t) + ".pickle"
+            print("save " + data_name)
+            with open(data_name, "wb") as f:
+                pickle.dump([results_all, args], f)
+            results_all = []
+    return results_all

@@ -289,6 +289,62 @@ class ControlAffineSystem:
             return xe_traj, rho_traj, margin
         return xe_traj, rho_traj
 
+    def compute_density_batch(self, xe0_list, xref_list, uref_list, dt, cutting=True, compute_density=True,
+                              log_density=False, stride=1):
+        """`compute_density` for R references in ONE kernel launch (dp_rollout_batch): reference r has its own
+        xref (1,5,T_r+1) / uref (1,2,T_r) and initial errors xe0 (n,5,1) (the same n for all).  This is how the raw-data
+        generator's 20-sample trajectories (data_generation/compute_rawdata.py:26) fill the GPU.
+        Returns a list of (xe_traj (n,5,Ts_r), rho_traj (n,1,Ts_r) or None), each exactly what `compute_density` returns
+        for that reference alone."""
+        L = _lib.lib()
+        dc = self.controller.controller
+        dev = dc.device
+        R = len(xe0_list)
+        if R == 0:
+            return []
+        out_dev = xe0_list[0].device
+        n = xe0_list[0].shape[0]
+        Ts_ref = [int(u.shape[2]) for u in uref_list]
+        T = max(Ts_ref)
+        xref = torch.zeros((R, 5, T + 1), dtype=torch.float32)
+        uref = torch.zeros((R, 2, T), dtype=torch.float32)
+        for r in range(R):
+            if xe0_list[r].shape[0] != n or xref_list[r].shape[2] != Ts_ref[r] + 1:
+                raise _lib.DensityPlannerError("compute_density_batch: inconsistent shapes for reference %d" % r)
+            xref[r, :, :Ts_ref[r] + 1] = xref_list[r][0].detach().cpu()
+            xref[r, :, Ts_ref[r] + 1:] = xref[r, :, Ts_ref[r]:Ts_ref[r] + 1]
+            uref[r, :, :Ts_ref[r]] = uref_list[r][0].detach().cpu()
+        xe0 = torch.cat([x.detach().reshape(n, 5).to(torch.float32).cpu() for x in xe0_list], dim=0)
+        flags = (_lib.DP_LOG_DENSITY if log_density else 0) | (_lib.DP_DENSITY if compute_density else 0) | \
+                (_lib.DP_CUT if cutting else 0)
+        Ts = T // stride + 1
+        N = R * n
+        xe0_d, xref_d, uref_d = xe0.to(dev), xref.to(dev), uref.to(dev)
+        t_ref = torch.tensor(Ts_ref, dtype=torch.int32, device=dev)
+        x_out = torch.empty((Ts, 5, N), dtype=torch.float32, device=dev)
+        rho_out = torch.empty((Ts, N), dtype=torch.float32, device=dev) if compute_density else None
+        st = torch.zeros(2, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.dp_rollout_batch(dc.handle, _lib.ptr(xe0_d), _lib.ptr(xref_d), _lib.ptr(uref_d), _lib.ptr(t_ref), None,
+                                          float(dt), R, n, T, flags, stride, _lib.ptr(x_out), _lib.ptr(rho_out), N, None,
+                                          _lib.ptr(st), _lib.current_stream(dev)), "dp_rollout_batch")
+        if compute_density and cutting:
+            status = st.tolist()
+            if status[0]:
+                print("clamp rho_traj to 1e30 (log density)" if log_density
+                      else "clamp rho_traj between 0 and 1e30 (no log density)")
+            if status[1]:
+                print("set nan in rho_traj to 1e30")
+        x_all = x_out.to(out_dev)
+        r_all = rho_out.to(out_dev) if compute_density else None
+        res = []
+        for r in range(R):
+            ts = Ts_ref[r] // stride + 1
+            xe = x_all[:ts, :, r * n:(r + 1) * n].permute(2, 1, 0)
+            rho = r_all[:ts, r * n:(r + 1) * n].unsqueeze(1).permute(2, 1, 0) if compute_density else None
+            res.append((xe, rho))
+        return res
+
     def get_valid_ref(self, args):
         """Rejection-sample a reference that stays admissible for > 99% of the horizon (:465-475)."""
         while True:

@@ -81,6 +81,18 @@ int dp_rollout(const dp_controller *c, const float *xe0, const float *xref, cons
                float dt, int64_t N, int T, unsigned flags, int stride, float *x_out, float *rho_out, int64_t ldn,
                float *clip_margin, int *status, void *stream);
 
+/*
+ * Several references in one launch (the raw-data generator's 20-sample trajectories,
+ * data_generation/compute_rawdata.py:26, cannot fill a GPU one at a time): R references with n_per_ref samples each.
+ *   xe0 dev [R*n_per_ref][5];  xref dev [R][5][T+1];  uref dev [R][2][T] (rows padded to the common T)
+ *   T_ref dev int[R] or NULL: horizon of every reference (<= T; slots beyond it are left untouched)
+ *   outputs as dp_rollout with N = R*n_per_ref samples, reference r owning samples [r*n_per_ref, (r+1)*n_per_ref)
+ * Tensor-core kernel only (every 128-sample tile belongs to one reference).
+ */
+int dp_rollout_batch(const dp_controller *c, const float *xe0, const float *xref, const float *uref, const int *T_ref,
+                     const float *rho0, float dt, int64_t R, int64_t n_per_ref, int T, unsigned flags, int stride,
+                     float *x_out, float *rho_out, int64_t ldn, float *clip_margin, int *status, void *stream);
+
 /* Same with HOST buffers (x_out/rho_out host, ld = N); status is a host int[2].  Copies are part of the call. */
 int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const float *uref, const float *rho0,
                     float dt, int64_t N, int T, unsigned flags, int stride, float *x_out, float *rho_out,

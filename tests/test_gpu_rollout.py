@@ -208,3 +208,37 @@ def test_compute_data_matches_reference_golden(dp, car, args):
         assert np.abs(r["xe_traj"].numpy() - g["r%d_xe_traj" % i]).max() < 1e-4
         ref = g["r%d_rholog_traj" % i]
         assert np.abs(r["rholog_traj"].numpy() - ref).max() < 1e-3 * np.abs(ref).max() + 1e-4
+
+
+def test_batched_references_equal_single_launches(dp, car, args):
+    """dp_rollout_batch: R references with their own horizons in one launch == R separate compute_density calls, bit for
+    bit (every tile belongs to one reference), for sample counts below, at and above one tile."""
+    torch.manual_seed(21)
+    refs = []
+    for r in range(5):
+        up, uref, xref = car.get_valid_ref(args)
+        T = 37 + 11 * r
+        refs.append((uref[:, :, :T], xref[:, :, :T + 1]))
+    for n in (20, 128, 150):
+        xe0s = [car.sample_xe0(n) for _ in refs]
+        outs = car.compute_density_batch(xe0s, [x for _, x in refs], [u for u, _ in refs], args.dt_sim, log_density=True)
+        for (uref, xref), xe0, (xe_b, rho_b) in zip(refs, xe0s, outs):
+            xe_s, rho_s = car.compute_density(xe0.cuda(), xref, uref, args.dt_sim, log_density=True, impl="tc")
+            assert xe_b.shape == xe_s.shape and rho_b.shape == rho_s.shape
+            assert bool((xe_b == xe_s.cpu()).all()) and bool((rho_b == rho_s.cpu()).all())
+
+
+def test_compute_data_batched_matches_reference_golden(dp, car, args):
+    """The batched raw-data generator (one launch per file) reproduces the reference's seeded output like compute_data."""
+    g = golden("compute_data.npz")
+    torch.manual_seed(5)
+    res = dp.compute_data_batched([1, 2], 20, car, args, samples_t=10, save=False)
+    assert len(res) == 2
+    for i, r in enumerate(res):
+        assert (r["u_params"].numpy() == g["r%d_u_params" % i]).all()
+        assert (r["xref0"].numpy() == g["r%d_xref0" % i]).all()
+        assert (r["t"].numpy() == g["r%d_t" % i]).all()
+        assert (r["xe0"].numpy() == g["r%d_xe0" % i]).all()
+        assert np.abs(r["xe_traj"].numpy() - g["r%d_xe_traj" % i]).max() < 1e-4
+        ref = g["r%d_rholog_traj" % i]
+        assert np.abs(r["rholog_traj"].numpy() - ref).max() < 1e-3 * np.abs(ref).max() + 1e-4
