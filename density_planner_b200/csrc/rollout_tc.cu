@@ -65,7 +65,8 @@ static_assert(SP_C1H + 64 == SMALL_NET_FLOATS, "small block layout");
 constexpr int OFF_Z = IMAGE_BYTES;                              // float [2 groups][36][128]: tz, A, B per z-row
 constexpr int OFF_PART = OFF_Z + NGROUPS * 36 * TILE * 4;       // float [2 groups][2 halves][4][128]
 constexpr int OFF_CB = OFF_PART + NGROUPS * 2 * 4 * TILE * 4;   // float4 [2 groups][2 nets][64 pairs]: {wz_j, wz_j1, cb_j, cb_j1}
-constexpr int OFF_BAR = OFF_CB + NGROUPS * 2 * 64 * 16;         // 2 mbarriers + tmem pointer
+constexpr int OFF_REF = OFF_CB + NGROUPS * 2 * 64 * 16;         // float [2 groups][3 slots][8]: xref[0..4], uref[0..1] of a time index
+constexpr int OFF_BAR = OFF_REF + NGROUPS * 3 * 8 * 4;          // 2 mbarriers + tmem pointer
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -73,16 +74,16 @@ constexpr float C2SCALE = INV_WSCALE * TWO_LOG2E;        // accumulator (x16) ->
 constexpr float INV_S2 = INV_WSCALE * INV_WSCALE;        // layer-3 tangent accumulators carry both x16 factors
 
 // optional in-kernel timeline (DP_TC_TRACE): CTA 0, lane 0 of warps {0, 7, 8, 15}, first TRACE_CHAINS chains
-constexpr int TRACE_CHAINS = 12, TRACE_EVENTS = 16, TRACE_WHO = 4;
-#define TRACE(ev)                                                                                                   \
-    do {                                                                                                            \
-        if (c.trace && c.tchain < TRACE_CHAINS) c.trace[(c.who * TRACE_CHAINS + c.tchain) * TRACE_EVENTS + (ev)] = clock64(); \
+constexpr int TRACE_CHAINS = 12, TRACE_EVENTS = 20, TRACE_WHO = 4;
+#define TRACE(ev)                                                                                                         \
+    do {                                                                                                                  \
+        if (TR && c.trace && c.tchain < TRACE_CHAINS) c.trace[(c.who * TRACE_CHAINS + c.tchain) * TRACE_EVENTS + (ev)] = clock64(); \
     } while (0)
 
 struct Ctx {
     unsigned long long *trace;  // null unless this thread records
     int who, tchain;
-    int grp, nchain;    // group index, chains completed by this group
+    int grp;            // group index
 
     uint32_t RA, RD;    // lane-0 TMEM addresses of the two regions (MMA operands / accumulators)
     uint32_t ra, rd;    // the same with this warp's lane offset (tcgen05.ld / st)
@@ -185,8 +186,18 @@ __device__ __forceinline__ float2 as_f2(uint32_t a, uint32_t b) { return make_fl
 // One net of one tile.  NET 0 = a (w1: 12x4 matrix, 48 outputs), NET 1 = b (w2: 2x12 matrix, 24 outputs).
 // Net a runs first and leaves per z-row r: tz = tanh(z_r), A_r = g_z dz_r/dtheta, B_r = g_z dz_r/dv in sZ;
 // net b then accumulates this thread's share (rows 6h .. 6h+5) of the head sums into acc[4] = {u0, u1, du0/dtheta, du1/dv}.
-template <int TP, int TOKEN, int KC>
-__device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const float4 in, const float4 xe, float (&acc)[4]) {
+struct SampleState {
+    float x0, x1, x2, x3, x4, rho, margin;
+};
+
+// error state of the controller (Controller.__call__, sytem_CAR.py:33-34) from the sample state and the reference row
+__device__ __forceinline__ float4 error_state(const SampleState &st, const float *ref) {
+    const float4 r = *reinterpret_cast<const float4 *>(ref);
+    return make_float4(st.x0 - r.x, st.x1 - r.y, __fadd_rn(__fsub_rn(st.x2, r.z), st.x4), st.x3 - r.w);
+}
+
+template <int TP, int KC, int TR>
+__device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const SampleState &st, const float *ref, float (&acc)[4]) {
     const int N3 = NET == 0 ? N3A : N3B;
     const float *sp = c.small + NET * SMALL_NET_FLOATS;
     const uint64_t w2h = make_bdesc(c.sbase + (NET == 0 ? OFF_W2A_HI : OFF_W2B_HI), B_LBO, B_SBO);
@@ -198,21 +209,15 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     const int h = c.h;
 
     // ---- L1: layer 1 on CUDA cores -> value operand in RA; gates g1 = 1 - h1^2 stay in registers ----------------------
-    // The first half of a chain (L1, C1) is bound by the MUFU pipe, the second half by the tensor pipe: the two groups
-    // pass a token so that one group's first half runs against the other group's second half instead of in lockstep.
-    if (TOKEN) {
-        if (c.grp == 0) {
-            if (c.nchain > 0) asm volatile("bar.sync 4, %0;" ::"n"(NTHREADS) : "memory");
-        } else {
-            asm volatile("bar.sync 3, %0;" ::"n"(NTHREADS) : "memory");
-        }
-    }
     TRACE(0);
     uint32_t g1[32];
     {
         const float4 *W1P = reinterpret_cast<const float4 *>(sp + SP_W1P);
         const float4 *CB = c.sCB + NET * 64;
-        const float2 ix = make_float2(in.x, in.x), iy = make_float2(in.y, in.y), iz = make_float2(in.z, in.z);
+        // network input of U_FUNC.forward (model_CAR.py:24): (theta, v, theta - xe2, v - xe3); the last one equals the
+        // reference speed for every sample and lives in the per-step constants
+        const float inz = st.x2 - __fadd_rn(__fsub_rn(st.x2, ref[2]), st.x4);
+        const float2 ix = make_float2(st.x2, st.x2), iy = make_float2(st.x3, st.x3), iz = make_float2(inz, inz);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int ch = 4 * h + i;
@@ -301,12 +306,6 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         }
     }
     TRACE(5);
-    if (TOKEN) {
-        if (c.grp == 0)
-            asm volatile("bar.arrive 3, %0;" ::"n"(NTHREADS) : "memory");
-        else
-            asm volatile("bar.arrive 4, %0;" ::"n"(NTHREADS) : "memory");
-    }
     if (!KC) {
         publish(c);
         issue(c, [&] { mma_value(c.RA + 64, c.RD, w3h, w3l, idesc3); });
@@ -323,6 +322,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     for (int i = 0; i < 4; ++i) ld8(c.ra + 8 * (4 * h + i), gst + 8 * i);
     if (NET == 0) {
         // w1 rows 6h .. 6h+5 (columns 24h .. 24h+23): z_r = w1[r,:] . xe, tz, g_z; A0 = g_z w1[r,2], B0 = g_z w1[r,3]
+        const float4 xe = error_state(st, ref);
         uint32_t v[24];
         ld8(c.ra + 64 + 24 * h, v);
         ld8(c.ra + 64 + 24 * h + 8, v + 8);
@@ -439,6 +439,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
 
     // ---- R56: layer-3 tangent outputs ---------------------------------------------------------------------------------------------
     if (NET == 0) {
+        const float4 xe = error_state(st, ref);
         uint32_t a[24], b[24];
         ld8(c.ra + 24 * h, a);
         ld8(c.ra + 24 * h + 8, a + 8);
@@ -479,16 +480,13 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         }
     }
     TRACE(15);
-    ++c.tchain;
-    ++c.nchain;
+    if (TR) ++c.tchain;
 }
 
-struct SampleState {
-    float x0, x1, x2, x3, x4, rho, margin;
-};
 
 // one Euler step of state and (log-)density from the head sums (get_next_x :124, get_next_rho(log) :136-157)
-__device__ __forceinline__ void sample_advance(const RolloutParams &p, SampleState &st, float u0r, float u1r, float pd0, float pd1) {
+__device__ __forceinline__ void sample_advance(const RolloutParams &p, SampleState &st, float u0r, float u1r, float pd0, float pd1,
+                                               float sn, float cs) {
     const float dt = p.dt;
     st.margin = fminf(st.margin, fminf(fabsf(fabsf(u0r) - 3.0f), fabsf(fabsf(u1r) - 3.0f)));
     if (p.flags & DP_DENSITY) {
@@ -501,15 +499,13 @@ __device__ __forceinline__ void sample_advance(const RolloutParams &p, SampleSta
             st.rho = __fadd_rn(st.rho, __fmul_rn(__fmul_rn(-div, st.rho), dt));
     }
     const float u0 = fminf(fmaxf(u0r, -3.0f), 3.0f), u1 = fminf(fmaxf(u1r, -3.0f), 3.0f);
-    float sn, cs;
-    sincosf(st.x2, &sn, &cs);
     st.x0 = __fadd_rn(st.x0, __fmul_rn(__fmul_rn(st.x3, cs), dt));
     st.x1 = __fadd_rn(st.x1, __fmul_rn(__fmul_rn(st.x3, sn), dt));
     st.x2 = __fadd_rn(st.x2, __fmul_rn(u0, dt));
     st.x3 = __fadd_rn(st.x3, __fmul_rn(u1, dt));
 }
 
-template <int TP, int TOKEN, int KC, int BATCH>
+template <int TP, int KC, int BATCH, int TR>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -550,10 +546,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
     c.sZ = reinterpret_cast<float *>(smem + OFF_Z) + grp * 36 * TILE;
     c.sCB = reinterpret_cast<const float4 *>(smem + OFF_CB) + grp * 2 * 64;
     c.who = (warp == 0) ? 0 : (warp == 7) ? 1 : (warp == 8) ? 2 : (warp == 15) ? 3 : -1;
-    c.trace = (p.trace && blockIdx.x == 0 && lane == 0 && c.who >= 0) ? p.trace : nullptr;
+    c.trace = (TR && p.trace && blockIdx.x == 0 && lane == 0 && c.who >= 0) ? p.trace : nullptr;
     c.tchain = 0;
     c.grp = grp;
-    c.nchain = 0;
     float *sPart = reinterpret_cast<float *>(smem + OFF_PART) + grp * 2 * 4 * TILE;
     uint32_t ph = 0;
 
@@ -568,15 +563,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
     // per-step constant part of the layer-1 pre-activation, W1[:,3] * in.w + b1 (in.w = xref[3][t] is the same for every
     // sample): thread k of the group owns (net k / 128, feature k % 128) and refreshes it once per step
     float *cb_mine;
-    float cb_w, cb_b;
+    const float *cb_wp, *cb_bp;
     {
         const int k = tid & (GT - 1), net = k >> 7, j = k & 127;
         const float *spn = c.small + net * SMALL_NET_FLOATS;
         float *cb4 = reinterpret_cast<float *>(smem + OFF_CB) + ((grp * 2 + net) * 64 + (j >> 1)) * 4;
         cb4[j & 1] = spn[SP_W1P + 8 * (j >> 1) + 4 + (j & 1)];  // W1[:,2] pair, static
         cb_mine = cb4 + 2 + (j & 1);
-        cb_w = spn[SP_W1P + 8 * (j >> 1) + 6 + (j & 1)];
-        cb_b = spn[SP_B1P + j];
+        cb_wp = spn + SP_W1P + 8 * (j >> 1) + 6 + (j & 1);
+        cb_bp = spn + SP_B1P + j;
     }
     const long long num_rounds = (num_tiles + NGROUPS - 1) / NGROUPS;
     for (long long round = blockIdx.x; round < num_rounds; round += gridDim.x) {
@@ -607,13 +602,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
         st.rho = p.rho0 ? __ldg(p.rho0 + nl) : (logd ? 0.0f : 1.0f);
         st.margin = 1e30f;
         int next_store = 0, slot = 0;
-        if (T > 0) {
-            *cb_mine = fmaf(cb_w, __ldg(xref + 3 * T1), cb_b);
-            group_sync(c.bar_id);
+        // The reference of a time index (5 states, 2 inputs) is read by every thread of the group.  L1 has no room next to
+        // 224 KB of shared memory, so every global load would be an L2 round trip on the step's critical path: lanes 0..6 of
+        // one warp fetch time index i + 2 with cp.async while step i runs (three slots), everybody reads shared memory.
+        float *sRef = reinterpret_cast<float *>(smem + OFF_REF) + grp * 3 * 8;
+        const int gk = tid & (GT - 1);
+        const bool fetcher = (gk >> 5) == 1 && lane < 7;  // second warp of the group (the first one issues the MMAs)
+        const float *fsrc = lane < 5 ? xref + lane * T1 : uref + (lane - 5) * p.T;
+        const int flim = lane < 5 ? T : T - 1;            // last valid time index of this element's row
+        group_sync(c.bar_id);  // the previous tile's last reads of sRef are done
+        if (gk < 16) {
+            const int e = gk & 7, t0 = gk >> 3;
+            float v = 0.0f;
+            if (e < 5 && t0 <= T) v = __ldg(xref + e * T1 + t0);
+            if (e >= 5 && e < 7 && t0 < T) v = __ldg(uref + (e - 5) * p.T + t0);
+            sRef[t0 * 8 + e] = v;
         }
+        if (T > 0) *cb_mine = fmaf(*cb_wp, __ldg(xref + 3 * T1), *cb_bp);
+        group_sync(c.bar_id);
         for (int i = 0;; ++i) {
-            const float xr0 = __ldg(xref + 0 * T1 + i), xr1 = __ldg(xref + 1 * T1 + i);
-            const float xr2 = __ldg(xref + 2 * T1 + i), xr3 = __ldg(xref + 3 * T1 + i);
+            if (fetcher && i + 2 <= flim)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sRef + ((i + 2) % 3) * 8 + lane)),
+                             "l"(fsrc + i + 2)
+                             : "memory");
+            const float4 rA = *reinterpret_cast<const float4 *>(sRef + (i % 3) * 8);
+            const float4 rB = *reinterpret_cast<const float4 *>(sRef + (i % 3) * 8 + 4);
+            const float xr0 = rA.x, xr1 = rA.y, xr2 = rA.z, xr3 = rA.w;
             if (i == next_store) {
                 // stored slice: the owner thread (h == 0) of each sample writes; a warp covers 32 consecutive samples per row
                 if (h == 0) {
@@ -641,7 +655,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
                                 if (nd == 5) {
                                     o[2 * p.ldn] = st.x2 - xr2;
                                     o[3 * p.ldn] = st.x3 - xr3;
-                                    o[4 * p.ldn] = st.x4 - __ldg(xref + 4 * T1 + i);
+                                    o[4 * p.ldn] = st.x4 - rB.x;
                                 }
                             }
                         }
@@ -652,35 +666,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
                 ++slot;
             }
             if (i == T) break;
-            // Controller.__call__ (sytem_CAR.py:33-34) and the network input of U_FUNC.forward (model_CAR.py:24)
-            const float e0 = st.x0 - xr0, e1 = st.x1 - xr1, e3 = st.x3 - xr3;
-            const float e2 = __fadd_rn(__fsub_rn(st.x2, xr2), st.x4);
-            const float4 in = make_float4(st.x2, st.x3, st.x2 - e2, st.x3 - e3);
-            const float4 xe = make_float4(e0, e1, e2, e3);
-            const float ur0 = __ldg(uref + i), ur1 = __ldg(uref + p.T + i);
-
+            // the chains take the controller's error state and network input from the sample state and the reference row
+            // in shared memory where they need them (nothing but the state stays in registers across a chain)
+            const float *ref = sRef + (i % 3) * 8;
             float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 1
             for (int net = 0; net < 2; ++net) {  // net a, then net b; the two TMEM regions swap roles
                 const uint32_t A = net == 0 ? R0 : R1, Dd = net == 0 ? R1 : R0;
                 c.RA = A; c.RD = Dd; c.ra = A + lane_off; c.rd = Dd + lane_off;
-                chain<TP, TOKEN, KC>(c, ph, net, in, xe, acc);
+                chain<TP, KC, TR>(c, ph, net, st, ref, acc);
             }
             // exchange the partial head sums of the two feature halves (fixed order: both threads get identical totals)
             float *mine = sPart + h * 4 * TILE + c.s;
             mine[0 * TILE] = acc[0]; mine[1 * TILE] = acc[1]; mine[2 * TILE] = acc[2]; mine[3 * TILE] = acc[3];
-            if (i + 1 < T) *cb_mine = fmaf(cb_w, __ldg(xref + 3 * T1 + i + 1), cb_b);  // every thread is past both L1 stages
+            if (i + 1 < T) *cb_mine = fmaf(*cb_wp, sRef[((i + 1) % 3) * 8 + 3], *cb_bp);  // every thread is past both L1 stages
+            TRACE(16);
+            asm volatile("cp.async.wait_all;" ::: "memory");  // time index i + 2 has landed (it had the whole step)
             fence_before();
             group_sync(c.bar_id);
+            TRACE(17);
             const float *p0 = sPart + c.s, *p1 = sPart + 4 * TILE + c.s;
             const float pu0 = p0[0 * TILE] + p1[0 * TILE], pu1 = p0[1 * TILE] + p1[1 * TILE];
             const float pd0 = p0[2 * TILE] + p1[2 * TILE], pd1 = p0[3 * TILE] + p1[3 * TILE];
-            sample_advance(p, st, pu0 + ur0, pu1 + ur1, pd0, pd1);
+            float sn, cs;
+            sincosf(st.x2, &sn, &cs);
+            sample_advance(p, st, pu0 + ref[5], pu1 + ref[6], pd0, pd1, sn, cs);
+            TRACE(18);
         }
         if (h == 0 && valid && p.clip_margin) p.clip_margin[n] = st.margin;
     }
 
-    if (TOKEN && grp == 0 && c.nchain > 0) asm volatile("bar.sync 4, %0;" ::"n"(NTHREADS) : "memory");  // the last hand-off
     fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -740,33 +755,34 @@ void dp_tc_release(dp_controller *c) {
 int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStream_t stream) {
     DP_REQUIRE(c->d_tc != nullptr, "DP_IMPL_TC: tensor-core weight image missing");
     static bool attr_set[64] = {};
-    static int variant = -1;  // tuning / A-B knob: DP_TC_VARIANT = 100 * k_chunked + 10 * tangent_products + token
+    static int variant = -1;  // tuning / A-B knob: DP_TC_VARIANT = 100 * K-chunking (0 off, 1 four batches, 2 two) + 10 * tangent products
     typedef void (*kern_t)(RolloutParams);
-    static const kern_t kerns[8] = {rollout_tc_kernel<1, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0>, rollout_tc_kernel<2, 0, 0, 0>,
-                                    rollout_tc_kernel<2, 1, 0, 0>, rollout_tc_kernel<1, 0, 1, 0>, rollout_tc_kernel<1, 0, 2, 0>,
-                                    rollout_tc_kernel<2, 0, 1, 0>, rollout_tc_kernel<2, 0, 2, 0>};
-    static const kern_t kern_batch = rollout_tc_kernel<1, 0, 1, 1>;  // several references per launch (dp_rollout_batch)
+    static const kern_t kerns[6] = {rollout_tc_kernel<1, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0>, rollout_tc_kernel<1, 2, 0, 0>,
+                                    rollout_tc_kernel<2, 0, 0, 0>, rollout_tc_kernel<2, 1, 0, 0>, rollout_tc_kernel<2, 2, 0, 0>};
+    static const kern_t kern_batch = rollout_tc_kernel<1, 1, 1, 0>;  // several references per launch (dp_rollout_batch)
+    static const kern_t kern_trace = rollout_tc_kernel<1, 1, 0, 1>;  // with the in-kernel timeline (DP_TC_TRACE)
     if (variant < 0) {
         const char *e = getenv("DP_TC_VARIANT");
-        const int v = e ? atoi(e) : 110;  // 100 * K-chunking (0 off, 1 four batches, 2 two batches) + 10 * tangent products + token
-        const int kc = v / 100, tp2 = ((v / 10) % 10 == 1) ? 0 : 2;
-        variant = kc == 0 ? tp2 + ((v % 10) ? 1 : 0) : 4 + tp2 + (kc == 2 ? 1 : 0);
+        const int v = e ? atoi(e) : 110;
+        const int kc = (v / 100) % 3, tp = ((v / 10) % 10 == 2) ? 1 : 0;
+        variant = 3 * tp + kc;
     }
     if (!attr_set[c->device & 63]) {
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < 6; ++k)
             DP_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         DP_CUDA(cudaFuncSetAttribute(kern_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        DP_CUDA(cudaFuncSetAttribute(kern_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_set[c->device & 63] = true;
     }
     const bool batch = p.R > 1 || p.T_ref != nullptr;
-    const kern_t kern = batch ? kern_batch : kerns[variant];
+    const char *trace_path = getenv("DP_TC_TRACE");  // diagnostic: dump an in-kernel clock64 timeline of CTA 0
+    const kern_t kern = batch ? kern_batch : (trace_path ? kern_trace : kerns[variant]);
     RolloutParams q = p;
     q.tc = c->d_tc;
     const long long num_tiles = (p.R > 1 || p.T_ref) ? p.R * ((p.n_per_ref + TILE - 1) / TILE) : (p.N + TILE - 1) / TILE;
     const long long want = (num_tiles + NGROUPS - 1) / NGROUPS;
     const int grid = (int)(want < c->num_sms ? want : c->num_sms);
-    const char *trace_path = getenv("DP_TC_TRACE");  // diagnostic: dump an in-kernel clock64 timeline of CTA 0
-    if (trace_path) {
+    if (trace_path && !batch) {
         const size_t n = (size_t)TRACE_WHO * TRACE_CHAINS * TRACE_EVENTS;
         DP_CUDA(cudaMalloc(&q.trace, n * 8));
         DP_CUDA(cudaMemsetAsync(q.trace, 0, n * 8, stream));
