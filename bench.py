@@ -214,6 +214,7 @@ def main():
         raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa_node = D.bind_to_gpu_numa_node(local_rank) if (world > 1 and not os.environ.get("DP_NO_NUMA_BIND")) else None
     L = dp.lib()
     args = dp.default_args()
     car = dp.Car(args, device=dev)
@@ -345,7 +346,7 @@ def main():
            "d2h_bytes_per_step": int(4 * (T + 1) * 6 * Ne),
            "api": "Car.compute_density(xe0, xref_traj, uref_traj, dt, log_density=True) with CPU tensors "
                   "(dp_rollout_host: H2D + kernel + D2H of the full (N,5,T+1)+(N,1,T+1) trajectory)",
-           "ms_per_step": 1e3 * t_e2e, "pinned_d2h_gbs_measured": d2h_gbs}
+           "ms_per_step": 1e3 * t_e2e, "pinned_d2h_gbs_measured": d2h_gbs, "numa_node_rank0": numa_node}
     del xe_traj, rho_traj
 
     # ---- collision cost / binning throughput on the stored slices (second half of the metric) ---------------------

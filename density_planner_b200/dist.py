@@ -35,6 +35,32 @@ def init_from_env(backend=None):
     return rank, world, local_rank
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and hence its pinned host buffers, first-touch) to the CPUs of the NUMA node the GPU hangs off.
+
+    With one process per GPU the host<->device copies of all ranks run at the same time; a rank whose pinned buffers sit
+    on the other socket pays the inter-socket link for every byte.  Best effort: returns the node or None."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev_id = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev_id)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def world_size():
     return dist.get_world_size() if dist.is_initialized() else 1
 
