@@ -70,6 +70,15 @@ constexpr int OFF_BAR = OFF_REF + NGROUPS * 3 * 8 * 4;          // 2 mbarriers +
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
+#ifndef DP_SPLIT_TRUNC
+#define DP_SPLIT_TRUNC 1
+#endif
+#if DP_SPLIT_TRUNC
+#define SPLIT split_h2_trunc
+#else
+#define SPLIT split_h2
+#endif
+
 constexpr float C2SCALE = INV_WSCALE * TWO_LOG2E;        // accumulator (x16) -> 2 log2(e) * pre-activation
 constexpr float INV_S2 = INV_WSCALE * INV_WSCALE;        // layer-3 tangent accumulators carry both x16 factors
 
@@ -237,7 +246,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                 tanh4(y[0], y[1], t[0], t[1]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    split_h2(t[e], av[pq + e], av[8 + pq + e]);
+                    SPLIT(t[e], av[pq + e], av[8 + pq + e]);
                     g1[8 * i + pq + e] = gate_of(t[e], av[pq + e]);
                 }
             }
@@ -285,7 +294,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                 tanh4(y0, y1, t[0], t[1]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    split_h2(t[e], av[pq + e], av[8 + pq + e]);
+                    SPLIT(t[e], av[pq + e], av[8 + pq + e]);
                     gs[8 * i + pq + e] = gate_of(t[e], av[pq + e]);
                 }
             }

@@ -180,6 +180,15 @@ __device__ __forceinline__ void split_h2(const float2 v, uint32_t &hi, uint32_t 
     hi = h2_bits(h);
     lo = pack_h2(d.x, d.y);
 }
+// The same split with the hi part formed by TRUNCATING the fp32 mantissa to fp16's 10 bits (one LOP3 per element on the
+// integer pipe instead of an fp16->fp32 conversion on the FMA pipe, which bounds the epilogues): hi is exactly
+// representable in fp16, lo = v - hi is exact in fp32 and at most one fp16 ulp of hi, so hi + lo carries >= 21 bits.
+__device__ __forceinline__ void split_h2_trunc(const float2 v, uint32_t &hi, uint32_t &lo) {
+    const float2 f = make_float2(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+    const float2 d = __fadd2_rn(v, make_float2(-f.x, -f.y));
+    hi = pack_h2(f.x, f.y);
+    lo = pack_h2(d.x, d.y);
+}
 // tanh gate 1 - t^2 of a packed fp16 pair, one HFMA2 (the gates only scale the fp16 tangent operands)
 __device__ __forceinline__ uint32_t gate_h2(const uint32_t hi) {
     const __half2 h = bits_h2(hi);
