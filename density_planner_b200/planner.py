@@ -6,36 +6,101 @@ Reference surface mirrored here:
   motion_planning/MotionPlanner.py       get_cost_coll:192-224
   motion_planning/MotionPlannerGrad.py   get_cost_coll_initialize:309-336
 
-The density-NN branch (use_nn=True) and the other cost terms stay with the reference.
+The density-NN branch (use_nn=True) is evaluated for all time points in one batched torch pass (`DensityNN`); the goal /
+bounds cost terms are kernel backed (grid.get_cost_goal / get_cost_bounds).
 """
 import torch
 
 from . import _lib, grid as _grid
 
 
+class DensityNN:
+    """The reference's density-predictor MLP (density_training/utils.py:8-40: 31 -> 7 x 150 ReLU -> 6) evaluated for ALL
+    prediction time points in one batched pass instead of one call per time point
+    (simulation_objects.py:280-287 calls get_nn_prediction 101 times; density_training/utils.py:161-180).
+
+    Plain torch on the caller's device (cuBLAS GEMMs on the GPU; a stock dense MLP, SURVEY section 8f row 2 -- not one of
+    the hand-written kernels), differentiable w.r.t. `up` and `xe0` like the reference's branch."""
+
+    def __init__(self, weights=None, device=None):
+        import os
+        import numpy as np
+        if weights is None:
+            weights = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "density_nn_default.npz")
+        z = np.load(weights) if isinstance(weights, str) else weights
+        n_layers = len([k for k in z.keys() if k.endswith(".weight")])
+        dev = torch.device(device) if device is not None else torch.device("cpu")
+        self.W = [torch.from_numpy(np.asarray(z["linear_list.%d.weight" % i], dtype="float32")).to(dev) for i in range(n_layers)]
+        self.b = [torch.from_numpy(np.asarray(z["linear_list.%d.bias" % i], dtype="float32")).to(dev) for i in range(n_layers)]
+        self.device = dev
+
+    def predict(self, xe0, xref0, up, t_vec):
+        """xe0 (N,5), xref0 (5,), up (1,2,10) or flat (20,), t_vec (Tn,) -> xe (N,5,Tn), rholog (N,1,Tn).
+
+        Input row layout of data_generation/utils.py:4-37,101-135: [xe0 (5) | xref0 (5) | t | u_params (20)]."""
+        dev = self.device
+        N, Tn = xe0.shape[0], t_vec.shape[0]
+        xe0 = xe0.to(dev, torch.float32)
+        head = torch.cat((xe0, xref0.to(dev, torch.float32).reshape(1, -1).expand(N, -1)), dim=1)       # (N, 10)
+        upf = up.to(dev, torch.float32).reshape(1, -1).expand(N, -1)                                     # (N, 20)
+        t = t_vec.to(dev, torch.float32)
+        rows = torch.cat((head.unsqueeze(0).expand(Tn, -1, -1), t.reshape(Tn, 1, 1).expand(-1, N, -1),
+                          upf.unsqueeze(0).expand(Tn, -1, -1)), dim=2).reshape(Tn * N, -1)                # (Tn*N, 31)
+        x = rows
+        for i in range(len(self.W) - 1):
+            x = torch.relu(torch.addmm(self.b[i], x, self.W[i].t()))
+        y = torch.addmm(self.b[-1], x, self.W[-1].t()).reshape(Tn, N, -1)                                # (Tn, N, 6)
+        return y[:, :, :5].permute(1, 2, 0), y[:, :, 5:6].permute(1, 2, 0)
+
+
 class EgoPredictor:
     """The part of `EgoVehicle` the LE prediction needs: system, start state, sample set (xe0, rho0)."""
 
-    def __init__(self, system, args, xref0, xe0, rho0):
+    def __init__(self, system, args, xref0, xe0, rho0, density_nn=None):
         self.system = system
         self.args = args
         self.xref0 = xref0
         self.xe0 = xe0
         self.rho0 = rho0
+        self.density_nn = density_nn  # DensityNN for the use_nn=True branch (optional)
 
     def predict_density(self, up, xref_traj, use_nn=False, xe0=None, rho0=None, compute_density=True):
         """LE prediction of the state and density trajectories (simulation_objects.py:253-304, use_nn=False).
 
         Returns x_traj (N,5,101) and rho_traj (N,1,1001): as in the reference, the states are subsampled by
         args.factor_pred while the density keeps the full time resolution (:293 vs :296-298)."""
-        if use_nn:
-            raise NotImplementedError("the density-NN predictor stays with the reference (SURVEY section 8f item 2)")
         if xe0 is None:
             xe0 = self.xe0
         if rho0 is None:
             rho0 = self.rho0
             assert rho0.shape[0] == xe0.shape[0]
         args = self.args
+        if use_nn:
+            if self.density_nn is None:
+                raise NotImplementedError("no DensityNN attached to this predictor (pass density_nn=DensityNN(...))")
+            n_sim = args.N_sim
+            if args.input_type == "discr10" and up.shape[2] != 10:
+                n_sim = up.shape[2] * (args.N_sim_max // 10) + 1
+                up = torch.cat((up, torch.zeros(up.shape[0], up.shape[1], 10 - up.shape[2], device=up.device)), dim=2)
+            elif args.input_type == "discr5" and up.shape[2] != 5:
+                n_sim = up.shape[2] * (args.N_sim_max // 5) + 1
+                up = torch.cat((up, torch.zeros(up.shape[0], up.shape[1], 5 - up.shape[2], device=up.device)), dim=2)
+            t_vec = torch.arange(0, args.dt_sim * n_sim - 0.001, args.dt_sim * args.factor_pred)
+            out_dev = xref_traj.device
+            xe_nn, rholog_nn = self.density_nn.predict(xe0[:, :, 0], self.xref0[0, :, 0], up, t_vec)
+            Tn = xref_traj.shape[2]
+            # the reference fills (N, 5, Tn) / (N, 1, Tn) buffers of the reference's length time point by time point (:281-287)
+            xe_traj = torch.zeros(xe0.shape[0], 5, Tn, device=xe_nn.device)
+            rho_log = torch.zeros(xe0.shape[0], 1, Tn, device=xe_nn.device)
+            k = min(Tn, xe_nn.shape[2])
+            xe_traj[:, :, :k] = xe_nn[:, :, :k]
+            rho_log[:, :, :k] = rholog_nn[:, :, :k]
+            rho_traj = None
+            if compute_density:
+                rho_max, _ = rho_log.max(dim=0)
+                rho_un = torch.exp(rho_log - rho_max.unsqueeze(0)) * rho0.to(rho_log.device).reshape(-1, 1, 1)
+                rho_traj = (rho_un / rho_un.sum(dim=0).unsqueeze(0)).to(out_dev)
+            return (xe_traj + xref_traj.to(xe_traj.device)).to(out_dev), rho_traj
         if args.input_type == "discr10" and up.shape[2] != 10:
             up = torch.cat((up, torch.zeros(up.shape[0], up.shape[1], 10 - up.shape[2])), dim=2)
         elif args.input_type == "discr5" and up.shape[2] != 5:
@@ -88,13 +153,19 @@ def attach(planner, device=None):
 
         planner.get_cost_coll_initialize = _init
     system = Car(ego.args, device=device)
-    pred = EgoPredictor(system, ego.args, ego.xref0, ego.xe0, ego.rho0)
+    nn = None
+    model = getattr(ego, "model", None)
+    if model is not None and hasattr(model, "state_dict"):
+        # the ego's own density-NN weights, evaluated for all time points in one batched pass on the GPU
+        nn = DensityNN(weights={k: v.detach().cpu().numpy() for k, v in model.state_dict().items()},
+                       device=system.controller.controller.device)
+    pred = EgoPredictor(system, ego.args, ego.xref0, ego.xe0, ego.rho0, density_nn=nn)
     ref_predict = ego.predict_density
 
     def _predict(up, xref_traj, use_nn=True, xe0=None, rho0=None, compute_density=True):
-        if use_nn:
+        if use_nn and nn is None:
             return ref_predict(up, xref_traj, use_nn=True, xe0=xe0, rho0=rho0, compute_density=compute_density)
-        return pred.predict_density(up, xref_traj, use_nn=False, xe0=xe0, rho0=rho0, compute_density=compute_density)
+        return pred.predict_density(up, xref_traj, use_nn=use_nn, xe0=xe0, rho0=rho0, compute_density=compute_density)
 
     ego.predict_density = _predict
 

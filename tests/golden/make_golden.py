@@ -328,6 +328,33 @@ def gen_planner_terms(car, args):
     save("planner_terms.npz", **out)
 
 
+def gen_density_nn(car, args):
+    """the density-NN branch of EgoVehicle.predict_density (simulation_objects.py:280-299,
+    density_training/utils.py:161-180): exports the default checkpoint's weights and mints outputs + gradient w.r.t. up."""
+    rh.install()
+    with rh.ref_cwd():
+        from motion_planning.example_objects import create_mp_task
+        sd, _, _ = torch.load(args.name_pretrained_nn, map_location="cpu", weights_only=False)
+    out_dir = os.path.join(ROOT, "density_planner_b200", "data")
+    np.savez(os.path.join(out_dir, "density_nn_default.npz"), **{k: v.numpy() for k, v in sd.items()})
+    torch.manual_seed(0)
+    np.random.seed(0)
+    with rh.ref_cwd():
+        ego = create_mp_task(args, 0)
+    g = torch.Generator().manual_seed(51)
+    up = (0.8 * torch.randn(1, 2, 10, generator=g)).requires_grad_(True)
+    uref_traj, xref_traj = car.up2ref_traj(ego.xref0, up, args, short=True)
+    with rh.ref_cwd():
+        x_traj, rho_traj = ego.predict_density(up, xref_traj, use_nn=True)
+    w = torch.randn(x_traj.shape, generator=g)
+    wr = torch.randn(rho_traj.shape, generator=g)
+    loss = (w * x_traj).sum() + 1e3 * (wr * rho_traj).sum()
+    loss.backward()
+    save("density_nn.npz", up=up.detach(), xref0=ego.xref0[0, :, 0], xe0=ego.xe0[:, :, 0], rho0=ego.rho0[:, 0, 0],
+         xref_short=xref_traj.detach(), x_traj=x_traj.detach(), rho_traj=rho_traj.detach()[:, 0, :], w=w, wr=wr[:, 0, :],
+         gup=up.grad.clone(), loss=loss.detach())
+
+
 def gen_data(car, args):
     """compute_data (data_generation/compute_rawdata.py:9) with a fixed seed: RNG-order golden (config 1)."""
     rh.install()
@@ -344,7 +371,7 @@ def gen_data(car, args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="weights,rollout,step,grid,env,data,planner")
+    ap.add_argument("--only", default="weights,rollout,step,grid,env,data,planner,nn")
     ap.add_argument("--env-seeds", default="0,1,2,3,4,5,6,7,8,9")
     a = ap.parse_args()
     which = a.only.split(",")
@@ -364,6 +391,8 @@ def main():
         gen_env(car, args, [int(s) for s in a.env_seeds.split(",")])
     if "planner" in which:
         gen_planner_terms(car, args)
+    if "nn" in which:
+        gen_density_nn(car, args)
     print("done in %.1f s" % (time.time() - t0))
 
 

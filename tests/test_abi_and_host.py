@@ -96,3 +96,41 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 s = open(os.path.join(dirpath, f)).read()
                 assert "dp_oracle" not in s and "ref_harness" not in s, f
+
+
+def test_density_nn_batched_matches_reference_golden():
+    """the density-NN branch of predict_density, all 101 time points in one batched pass, against the
+    reference's 101-call loop (forward, normalised density and the gradient w.r.t. the input parameters).  Plain torch:
+    runs on the CPU here and on the GPU in the gpu suite."""
+    import types
+    import torch
+    import density_planner_b200 as dp
+    from conftest import golden
+    g = golden("density_nn.npz")
+    args = dp.default_args()
+    nn = dp.DensityNN()
+    system = types.SimpleNamespace()
+    pred = dp.EgoPredictor(system, args, torch.from_numpy(g["xref0"]).reshape(1, 5, 1), torch.from_numpy(g["xe0"]).unsqueeze(-1),
+                           torch.from_numpy(g["rho0"]).reshape(-1, 1, 1), density_nn=nn)
+    up = torch.from_numpy(g["up"]).requires_grad_(True)
+    xref = torch.from_numpy(g["xref_short"])
+    x_traj, rho_traj = pred.predict_density(up, xref, use_nn=True)
+    assert x_traj.shape == g["x_traj"].shape and rho_traj.shape == (g["rho_traj"].shape[0], 1, g["rho_traj"].shape[1])
+    assert np.abs(x_traj.detach().numpy() - g["x_traj"]).max() < 1e-4
+    ref = g["rho_traj"]
+    got = rho_traj.detach()[:, 0, :].numpy()
+    assert np.abs(got - ref).max() < 1e-4 * ref.max()
+    loss = (torch.from_numpy(g["w"]) * x_traj).sum() + 1e3 * (torch.from_numpy(g["wr"]).unsqueeze(1) * rho_traj).sum()
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 2e-4 * abs(float(g["loss"]))
+    # x_traj = xe_nn + xref and the golden differentiates through the reference integrator as well (xref depends on up):
+    # that part comes from the oracle's adjoint with the upstream gradient w summed over the samples
+    import dp_oracle as O
+    uref_long = np.repeat(g["up"], 100, axis=2)[:, :, :1000]
+    xref_long = O.xref_traj(g["xref0"], uref_long, 0.01)
+    gx = np.zeros((1, 5, 1001))
+    gx[0, :, ::10] = g["w"].sum(axis=0)
+    gu, _ = O.xref_traj_grad(xref_long, gx, 0.01)
+    gup_int = gu.reshape(1, 2, 10, 100).sum(axis=3)
+    total = up.grad.numpy() + gup_int
+    assert np.abs(total - g["gup"]).max() < 2e-3 * np.abs(g["gup"]).max()

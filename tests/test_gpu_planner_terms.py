@@ -116,3 +116,18 @@ def test_attach_binds_the_kernel_backed_calls(dp, oracle, args):
     cb, inb = planner.get_cost_bounds(xs, rs, evaluate=False, get_max=False)
     assert cg.device.type == "cpu" and abs(float(cg) - float(pt["goal_e0_m0"])) <= 1e-4 * float(pt["goal_e0_m0"])
     assert abs(float(cb) - float(pt["bounds_e0_m0"][0])) <= 1e-4 * float(pt["bounds_e0_m0"][0]) and not bool(inb)
+
+
+def test_density_nn_on_gpu_matches_reference_golden(dp, args):
+    """The batched density-NN branch on the GPU (cuBLAS fp32) against the reference's 101-call loop."""
+    import types
+    g = golden("density_nn.npz")
+    nn = dp.DensityNN(device="cuda")
+    pred = dp.EgoPredictor(types.SimpleNamespace(), args, torch.from_numpy(g["xref0"]).reshape(1, 5, 1),
+                           torch.from_numpy(g["xe0"]).unsqueeze(-1), torch.from_numpy(g["rho0"]).reshape(-1, 1, 1), density_nn=nn)
+    up = torch.from_numpy(g["up"]).requires_grad_(True)
+    x_traj, rho_traj = pred.predict_density(up, torch.from_numpy(g["xref_short"]), use_nn=True)
+    assert x_traj.device.type == "cpu" and np.abs(x_traj.detach().numpy() - g["x_traj"]).max() < 1e-4
+    assert np.abs(rho_traj.detach()[:, 0, :].numpy() - g["rho_traj"]).max() < 1e-4 * g["rho_traj"].max()
+    (torch.from_numpy(g["w"]) * x_traj).sum().backward()
+    assert up.grad is not None and bool(torch.isfinite(up.grad).all())
