@@ -18,6 +18,9 @@
 //     one group waits for its MMAs the other group's epilogue math fills the issue slots, and vice versa.
 //   * no MMA warp: after the group's named barrier, one elected thread of the group's first warp issues the group's
 //     tcgen05.mma batch and commits it to the group's mbarrier; everybody in the group then waits on that mbarrier.
+//     M1, M4 and M2 are K-CHUNKED: in iteration i of the producing loop the other warps only ARRIVE on a chunk barrier
+//     and go on, the first warp waits for them and issues K-chunks {i, 4 + i}: the tensor pipe works through a batch
+//     while the CUDA cores are still producing the rest of its operand.
 //   * chain for one (tile, net), RA / RD = the group's two regions (they swap roles from one chain to the next):
 //       L1    CUDA cores: h1 = tanh(W1 in + b1) -> RA (value operand hi/lo, 128 cols); layer-1 gates g1 in registers
 //       M1    D = W2 h1 (3 products)                                RA -> RD (128 fp32 accumulator columns)
@@ -31,10 +34,15 @@
 //       M5+M6 layer-3 tangents                                      RD[0:64) -> RA[0:N3), RD[64:128) -> RA[N3:2 N3)
 //       R56   read the tangent outputs; head sums
 //     Every operand is overwritten only after the MMA batch that read it has been committed and waited for.
-//   * the epilogue math is packed fp32x2 (FFMA2 / FADD2) with pre-scaled biases: pre-activations arrive already
-//     multiplied by 2 log2(e), tanh = 1 - 2 / (1 + 2^y) with MUFU.EX2 + MUFU.RCP.
+//   * the epilogue math is packed fp32x2 (FFMA2 / FADD2 / FMUL2) with pre-scaled biases: pre-activations arrive already
+//     multiplied by 2 log2(e); tanh|x| = 2 / (1 + 2^-|y|) - 1 with the sign copied from y, four reciprocals share one
+//     MUFU.RCP (tc_ptx.cuh).  The part of the layer-1 pre-activation that is the same for every sample of a time index
+//     is computed once per step per group.
 //   * both threads of a sample (feature halves h = 0, 1) carry the sample state redundantly in registers, so the Euler
 //     step needs one exchange of four partial head sums through shared memory and no broadcast of the next input.
+//   * 224 KB of shared memory leave the L1 no room: every global load and every register spill reload is an L2 round
+//     trip.  The reference rows are therefore prefetched into shared memory with cp.async two time indices ahead, and the
+//     chains derive their inputs from the sample state instead of keeping them in registers.
 #include <stdlib.h>
 
 #include <vector>
@@ -50,7 +58,8 @@ constexpr int GT = GW * 32;       // threads per group
 constexpr int NGROUPS = 2;
 constexpr int NTHREADS = NGROUPS * GT;
 // kernel variants (template parameters): TP = tangent products (2: fp16 tangent activations x (hi + lo) weights; 1: hi
-// weights only), TOKEN = hand-off of the MUFU-heavy half of a chain between the two groups (0 off, 1 on)
+// weights only, the default), KC = K-chunked MMA issue (0 off, 1 four batches, 2 two batches), BATCH = several references
+// per launch (dp_rollout_batch), TR = in-kernel clock64 timeline (DP_TC_TRACE)
 
 // per-net fp32 block of the operand image (this kernel's own layout of the "small" section)
 constexpr int SP_W1P = 0;    // [64 pairs][8]: {wx_j, wx_j1, wy_j, wy_j1 | wz_j, wz_j1, ww_j, ww_j1} * 2 log2(e)
