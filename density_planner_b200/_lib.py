@@ -60,6 +60,7 @@ _SIGNATURES = {
     "dp_normalize_apply": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp]),
     "dp_probe_ffma_peak": (_int, [_int, ctypes.POINTER(ctypes.c_double)]),
     "dp_tc_mma_bench": (_int, [_int, _int, _int, _int, ctypes.POINTER(ctypes.c_double)]),
+    "dp_tc_tmem_bench": (_int, [_int, _int, _int, ctypes.POINTER(ctypes.c_double)]),
     "dp_tc_selftest": (_int, [_int, _vp, _vp, _int, _int, _int, _f32, _vp]),
 }
 

@@ -58,7 +58,7 @@ constexpr int GT = GW * 32;       // threads per group
 constexpr int NGROUPS = 2;
 constexpr int NTHREADS = NGROUPS * GT;
 // kernel variants (template parameters): TP = tangent products (2: fp16 tangent activations x (hi + lo) weights; 1: hi
-// weights only, the default), KC = K-chunked MMA issue (0 off, 1 four batches, 2 two batches), BATCH = several references
+// weights only, the default), KC = K-chunked MMA issue (0 off, 1 for M1, M4 and M2, 2 for M1 and M4 only: the default), BATCH = several references
 // per launch (dp_rollout_batch), TR = in-kernel clock64 timeline (DP_TC_TRACE)
 
 // per-net fp32 block of the operand image (this kernel's own layout of the "small" section)
@@ -260,16 +260,9 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                 }
             }
             st16(c.ra + 16 * ch, av);
-            if (KC == 1)
+            if (KC >= 1)
                 chunk_issue(c, i, i == 3, [&] {
                     mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, i, i == 0);
-                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 4 + i, false);
-                });
-            if (KC == 2 && (i & 1))  // two batches of four K-chunks
-                chunk_issue(c, i, i == 3, [&] {
-                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, i - 1, i == 1);
-                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, i, false);
-                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 3 + i, false);
                     mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 4 + i, false);
                 });
         }
@@ -309,16 +302,9 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
             }
             st16(c.rd + 16 * ch, av);
             st8(c.ra + 8 * ch, &g1[8 * i]);
-            if (KC == 1)
+            if (KC >= 1)
                 chunk_issue(c, i, i == 3, [&] {
                     mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, i, i == 0);
-                    mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, 4 + i, false);
-                });
-            if (KC == 2 && (i & 1))
-                chunk_issue(c, i, i == 3, [&] {
-                    mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, i - 1, i == 1);
-                    mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, i, false);
-                    mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, 3 + i, false);
                     mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, 4 + i, false);
                 });
         }
@@ -406,17 +392,10 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                     mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, i, i == 0);
                     mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, 4 + i, false);
                 });
-            if (KC == 2 && (i & 1))
-                chunk_issue(c, i, i == 3, [&] {
-                    mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, i - 1, i == 1);
-                    mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, i, false);
-                    mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, 3 + i, false);
-                    mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, 4 + i, false);
-                });
         }
     }
     TRACE(8);
-    if (!KC) {
+    if (KC != 1) {  // KC == 2: M2 (eight short MMAs) in one batch, without the four chunk barriers
         publish(c);
         issue(c, [&] { mma_tangent<TP>(c.RA, c.RD, w2h, w2l, idesc128); });
     }
@@ -777,11 +756,11 @@ int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStr
     typedef void (*kern_t)(RolloutParams);
     static const kern_t kerns[6] = {rollout_tc_kernel<1, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0>, rollout_tc_kernel<1, 2, 0, 0>,
                                     rollout_tc_kernel<2, 0, 0, 0>, rollout_tc_kernel<2, 1, 0, 0>, rollout_tc_kernel<2, 2, 0, 0>};
-    static const kern_t kern_batch = rollout_tc_kernel<1, 1, 1, 0>;  // several references per launch (dp_rollout_batch)
-    static const kern_t kern_trace = rollout_tc_kernel<1, 1, 0, 1>;  // with the in-kernel timeline (DP_TC_TRACE)
+    static const kern_t kern_batch = rollout_tc_kernel<1, 2, 1, 0>;  // several references per launch (dp_rollout_batch)
+    static const kern_t kern_trace = rollout_tc_kernel<1, 2, 0, 1>;  // with the in-kernel timeline (DP_TC_TRACE)
     if (variant < 0) {
         const char *e = getenv("DP_TC_VARIANT");
-        const int v = e ? atoi(e) : 110;
+        const int v = e ? atoi(e) : 210;
         const int kc = (v / 100) % 3, tp = ((v / 10) % 10 == 2) ? 1 : 0;
         variant = 3 * tp + kc;
     }

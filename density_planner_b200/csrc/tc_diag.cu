@@ -173,7 +173,74 @@ __global__ void __launch_bounds__(64, 1) tc_mma_bench_kernel(int variant, int n,
     }
 }
 
+// ---- diagnostic: TMEM load / store throughput with all 16 warps of a CTA busy (what the epilogues see) ------------------------
+// mode 0: tcgen05.ld 32x32b.x16 back to back (one wait per 4), mode 1: tcgen05.st 32x32b.x16, mode 2: ld + dependent st
+__global__ void __launch_bounds__(512, 1) tc_tmem_bench_kernel(int mode, int iters, long long *out) {
+    __shared__ uint32_t tmem_ptr;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tm = tmem_ptr + ((uint32_t)(32 * (warp & 3)) << 16) + 128u * (warp >> 2);
+    uint32_t r[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) r[k] = tid + k;
+    st16(tm, r);
+    wait_st();
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (mode == 0) {
+                ld16(tm + 16 * j, r);
+            } else if (mode == 1) {
+                st16(tm + 16 * j, r);
+            } else {
+                ld16(tm + 16 * j, r);
+                wait_ld();
+                r[0] += 1;
+                st16(tm + 16 * j + 64, r);
+            }
+        }
+        if (mode == 0) wait_ld();
+        if (mode != 0) wait_st();
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    if (tid == 0) out[0] = t1 - t0;
+    if (r[3] == 0x7fffffff) out[1] = r[5];
+    fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_ptr), "r"(512) : "memory");
+    }
+}
+
 }  // namespace
+
+// Diagnostic: cycles per warp-level tcgen05.ld / st (32x32b.x16 = 2 KB) with 16 warps of one CTA issuing concurrently.
+extern "C" int dp_tc_tmem_bench(int device, int mode, int iters, double *cycles_per_op) {
+    DP_REQUIRE(cycles_per_op && mode >= 0 && mode <= 2 && iters > 0, "dp_tc_tmem_bench: bad argument");
+    DeviceGuard guard(device);
+    long long *d;
+    DP_CUDA(cudaMalloc(&d, 16));
+    DP_CUDA(cudaMemset(d, 0, 16));
+    tc_tmem_bench_kernel<<<1, 512>>>(mode, iters, d);
+    DP_CUDA(cudaGetLastError());
+    DP_CUDA(cudaDeviceSynchronize());
+    long long h[2];
+    DP_CUDA(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *cycles_per_op = (double)h[0] / (4.0 * iters);  // per warp-level instruction, 16 warps in flight
+    return 0;
+}
 
 // Diagnostic export: one 128 x n x 128 product through the same TMEM-operand MMA path the rollout uses.
 // A host fp32 [128][128], W host fp32 [n_valid][128] (zero-padded to n rows), D host fp32 [128][n] = A * (scale*W)^T.

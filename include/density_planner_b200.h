@@ -235,6 +235,10 @@ int dp_tc_selftest(int device, const float *A, const float *W, int n_valid, int 
  * SWIZZLE_128B, 2: A and B in shared memory no swizzle, 3: both SWIZZLE_128B.  out[0] issue, out[1] completion. */
 int dp_tc_mma_bench(int device, int variant, int n, int iters, double *out);
 
+/* Diagnostic: cycles per warp-level tcgen05.ld (mode 0) / tcgen05.st (mode 1) / dependent ld+st pair (mode 2) of shape
+ * 32x32b.x16 (2 KB per warp) while all 16 warps of one 512-thread CTA issue them: the TMEM bandwidth the epilogues see. */
+int dp_tc_tmem_bench(int device, int mode, int iters, double *cycles_per_op);
+
 /* FP32 FFMA peak probe (measures the CUDA-core roofline the fp32 kernel is bounded by); returns TFLOP/s in *tflops */
 int dp_probe_ffma_peak(int device, double *tflops);
 
