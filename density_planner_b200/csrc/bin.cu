@@ -67,7 +67,7 @@ __device__ __forceinline__ void sample_cell(const BinArgs &a, float x, float y, 
 // The int64 mass of a window cell is kept as two 32-bit words: a native 32-bit shared-memory atomic on the low word returns
 // the old value, which tells exactly whether this addition carried into the high word (a 64-bit shared atomicAdd would
 // be a compare-and-swap loop that degrades under the contention of a tight sample cloud).
-template <int MODE>
+template <int MODE, bool VEC>
 __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
     extern __shared__ __align__(16) unsigned char bsm[];
     unsigned *slo = reinterpret_cast<unsigned *>(bsm);
@@ -84,8 +84,9 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
     int *count = a.count ? a.count + (long long)t * cells : nullptr;
     const float4 *tab = a.table ? a.table + (size_t)t * a.egx * a.egy : nullptr;
     // this block's samples: a contiguous chunk of the slice
-    const long long chunk = (a.N + gridDim.x - 1) / gridDim.x;
-    const long long n_lo = (long long)blockIdx.x * chunk, n_hi = min(n_lo + chunk, a.N);
+    long long chunk = (a.N + gridDim.x - 1) / gridDim.x;
+    if (VEC) chunk = (chunk + 3) & ~3LL;
+    const long long n_lo = min((long long)blockIdx.x * chunk, a.N), n_hi = min(n_lo + chunk, a.N);
     // window origin: mean cell of 32 probe samples spread over the chunk (any choice gives the same integer grids)
     if (tid < 32) {
         int ix = 0, iy = 0, ok = 0;
@@ -115,19 +116,17 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
     __syncthreads();
     const int ox = sorg[0], oy = sorg[1];
     double dot = 0.0;
-    const long long span = n_hi - n_lo;
-    const long long nmax = ((span + 31) / 32) * 32;  // keep warps converged for the match/redux collectives
-    for (long long k = tid; k < nmax; k += BIN_THREADS) {
-        const long long n = n_lo + k;
+    // one sample: window cell -> shared atomics; outside the window -> warp-aggregated global atomics (all lanes take part
+    // in the collectives, `live` tells whether this lane carries a sample)
+    auto put = [&](bool live, float x, float y, float w) {
         int cell = -1, wcell = -1;
         long long q = 0;
-        if (k < span) {
-            const float x = __ldg(xp + n * a.sx_n), y = __ldg(yp + n * a.sx_n);
+        if (live) {
             int ix, iy;
             sample_cell<MODE>(a, x, y, ix, iy);
             if (ix >= 0 && iy >= 0) {
                 // w * 2^s is exact in fp32 (power-of-two scale), so this equals llrint((double)w * 2^s)
-                q = wp ? __float2ll_rn(__fmul_rn(__ldg(wp + n * a.sw_n), a.scale_f)) : (long long)a.scale;
+                q = wp ? __float2ll_rn(__fmul_rn(w, a.scale_f)) : (long long)a.scale;
                 const int wx = ix - ox, wy = iy - oy;
                 if (wx >= 0 && wx < WIN && wy >= 0 && wy < WIN)
                     wcell = wx * WIN + wy;
@@ -145,19 +144,54 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
             }
             if (count) atomicAdd(scount + wcell, 1);
         }
-        // samples outside the window: lanes with the same cell elect a leader that issues the global atomics for the group
         if (__any_sync(0xffffffffu, cell >= 0)) {
             const unsigned grp = __match_any_sync(0xffffffffu, cell);
             const int leader = __ffs(grp) - 1;
             const unsigned lo = (unsigned)(q & 0xFFFFFF), mid = (unsigned)((q >> 24) & 0xFFFFFF);
             const int hi = (int)(q >> 48);
-            const unsigned slo = __reduce_add_sync(grp, lo), smid = __reduce_add_sync(grp, mid);
-            const int shi = __reduce_add_sync(grp, hi);
+            const unsigned rlo = __reduce_add_sync(grp, lo), rmid = __reduce_add_sync(grp, mid);
+            const int rhi = __reduce_add_sync(grp, hi);
             if (cell >= 0 && (int)(tid & 31) == leader) {
-                const long long sum = (long long)slo + ((long long)smid << 24) + ((long long)shi << 48);
+                const long long sum = (long long)rlo + ((long long)rmid << 24) + ((long long)rhi << 48);
                 if (mass) atomicAdd(reinterpret_cast<unsigned long long *>(mass + cell), (unsigned long long)sum);
                 if (count) atomicAdd(count + cell, __popc(grp));
             }
+        }
+    };
+    const long long span = n_hi - n_lo;
+    if (VEC) {
+        // contiguous, 16-byte aligned rows (chunk boundaries are multiples of four): LDG.128 of x, y, w, four samples per
+        // thread and iteration
+        const long long g_lo = n_lo >> 2, g_hi = n_hi >> 2;  // full groups of four
+        const long long gmax = g_lo + (((g_hi - g_lo) + 31) / 32) * 32;
+        for (long long g = g_lo + tid; g < gmax; g += BIN_THREADS) {
+            const bool live = g < g_hi;
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = xv, wv = xv;
+            if (live) {
+                xv = __ldg(reinterpret_cast<const float4 *>(xp) + g);
+                yv = __ldg(reinterpret_cast<const float4 *>(yp) + g);
+                if (wp) wv = __ldg(reinterpret_cast<const float4 *>(wp) + g);
+            }
+            put(live, xv.x, yv.x, wv.x);
+            put(live, xv.y, yv.y, wv.y);
+            put(live, xv.z, yv.z, wv.z);
+            put(live, xv.w, yv.w, wv.w);
+        }
+        // the last block of the slice also takes the (at most three) samples behind the last full group
+        const long long t_lo = g_hi << 2;
+        const bool tail = (n_hi == a.N) && (n_lo < a.N) && tid < 32;
+        if (tail && __any_sync(0xffffffffu, t_lo + tid < a.N)) {
+            const long long n = t_lo + tid;
+            const bool live = n < a.N;
+            put(live, live ? __ldg(xp + n) : 0.f, live ? __ldg(yp + n) : 0.f, (live && wp) ? __ldg(wp + n) : 0.f);
+        }
+    } else {
+        const long long nmax = ((span + 31) / 32) * 32;  // keep warps converged for the match/redux collectives
+        for (long long k = tid; k < nmax; k += BIN_THREADS) {
+            const long long n = n_lo + k;
+            const bool live = k < span;
+            put(live, live ? __ldg(xp + n * a.sx_n) : 0.f, live ? __ldg(yp + n * a.sx_n) : 0.f,
+                (live && wp) ? __ldg(wp + n * a.sw_n) : 0.f);
         }
     }
     __syncthreads();
@@ -318,14 +352,21 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
     }
     static bool attr_set = false;
     if (!attr_set) {
-        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
-        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
         attr_set = true;
     }
-    if (a.mode == 0)
-        bin2d_kernel<0><<<dim3((unsigned)B, (unsigned)Ts), BIN_THREADS, BIN_SMEM, stream>>>(a);
+    auto al16 = [](const void *p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
+    const bool vec = a.mode == 0 && sx_n == 1 && (!w || sw_n == 1) && al16(x) && al16(y) && al16(w) && sx_t % 4 == 0 &&
+                     (!w || sw_t % 4 == 0);
+    const dim3 grid((unsigned)B, (unsigned)Ts);
+    if (a.mode == 1)
+        bin2d_kernel<1, false><<<grid, BIN_THREADS, BIN_SMEM, stream>>>(a);
+    else if (vec)
+        bin2d_kernel<0, true><<<grid, BIN_THREADS, BIN_SMEM, stream>>>(a);
     else
-        bin2d_kernel<1><<<dim3((unsigned)B, (unsigned)Ts), BIN_THREADS, BIN_SMEM, stream>>>(a);
+        bin2d_kernel<0, false><<<grid, BIN_THREADS, BIN_SMEM, stream>>>(a);
     DP_CUDA(cudaGetLastError());
     if (occ_dot) {
         bin_dot_finalize_kernel<<<(Ts + 127) / 128, 128, 0, stream>>>(partial, a.B, Ts, 1.0 / a.scale, occ_dot);
