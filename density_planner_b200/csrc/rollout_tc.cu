@@ -509,26 +509,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
     const int grp = warp / GW, wl = warp % GW, q = wl & 3, h = wl >> 2;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
     uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 32);
-    {
-        const int4 *src = reinterpret_cast<const int4 *>(p.tc);
-        int4 *dst = reinterpret_cast<int4 *>(smem);
-        for (int i = tid; i < IMAGE_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
-    }
+    // operand image -> shared memory with the bulk-copy engine (TMA, cp.async.bulk): one thread arms an mbarrier with the
+    // byte count and issues the copies; the data arrives through the async proxy, which is also the proxy tcgen05.mma reads
+    // the weights through
     if (tid == 0) {
         mbar_init(smem_u32(bars), 1);
         mbar_init(smem_u32(bars + 1), 1);
+        mbar_init(smem_u32(bars + 2), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t lb = smem_u32(bars + 2);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lb), "r"((uint32_t)IMAGE_BYTES) : "memory");
+        constexpr int PIECE = 32768;
+        for (int off = 0; off < IMAGE_BYTES; off += PIECE) {
+            const int bytes = IMAGE_BYTES - off < PIECE ? IMAGE_BYTES - off : PIECE;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(smem + off)),
+                         "l"(reinterpret_cast<const unsigned char *>(p.tc) + off), "r"(bytes), "r"(lb)
+                         : "memory");
+        }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // make the generic-proxy writes of the weight image visible to the async proxy (tcgen05.mma reads smem through it)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     fence_before();
     __syncthreads();
     fence_after();
+    mbar_wait(smem_u32(bars + 2), 0);  // the image has landed
     const uint32_t tm = *tmem_ptr_s;
 
     Ctx c;
