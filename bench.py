@@ -474,8 +474,9 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": opts.steps, "warmup": max(opts.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "CAR rollout + Liouville density, %d samples x %d steps per GPU (BASELINE config 2), "
-                                   "then normaliser + collision cost + occupancy binning on %d stored slices" % (N, T, Ts),
+            "config": {"workload": "CAR rollout + Liouville density, %d samples x %d steps per GPU (%s), "
+                                   "then normaliser + collision cost + occupancy binning on %d stored slices" % (
+                                       N, T, "BASELINE config 2" if N == SAMPLES else "BASELINE config 5 scale: --samples", Ts),
                        "samples_per_gpu": N, "horizon_steps": T, "stored_slices": Ts,
                        "controller": "trained C3M controller_CAR_3layers (43,592 fp32 weights)",
                        "l2_policy": "inputs+outputs per step (%.0f MB written) exceed the 126 MB L2" % (4e-6 * Ts * 6 * N),
