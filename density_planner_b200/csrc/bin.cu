@@ -350,7 +350,10 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
         a.egy = env->geom.gy;
         a.partial = partial;
     }
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};
+    int cur_dev = 0;
+    DP_CUDA(cudaGetDevice(&cur_dev));
+    bool &attr_set = attr_set_dev[cur_dev & 63];
     if (!attr_set) {
         DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
         DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
