@@ -19,10 +19,11 @@
 //   * no MMA warp: after the group's named barrier, one elected thread of the group's first warp issues the group's
 //     tcgen05.mma batch and commits it to the group's mbarrier; everybody in the group then waits on that mbarrier.
 //     M1, M4 and M2 are K-CHUNKED: in iteration i of the producing loop the other warps only ARRIVE on a chunk barrier
-//     and go on, the first warp waits for them and issues K-chunks {i, 4 + i}: the tensor pipe works through a batch
+//     and go on, the first warp waits for them and issues the K-chunks completed there: the tensor pipe works through a batch
 //     while the CUDA cores are still producing the rest of its operand.
 //   * chain for one (tile, net), RA / RD = the group's two regions (they swap roles from one chain to the next):
-//       L1    CUDA cores: h1 = tanh(W1 in + b1) -> RA (value operand hi/lo, 128 cols); layer-1 gates g1 in registers
+//       L1    CUDA cores: h1 = tanh(W1 in + b1) -> RA (value operand hi/lo, 128 cols); the gates g1 = 1 - h1^2 are
+//             recomputed from the thread's own operand chunks while M1 drains (nothing of them is live during the tanh work)
 //       M1    D = W2 h1 (3 products)                                RA -> RD (128 fp32 accumulator columns)
 //       C1    per 16-feature chunk: drain RD, h2 = tanh(.), write h2 hi/lo IN PLACE of the drained accumulator chunk
 //             (RD becomes the layer-3 value operand); park g1 in RA[0:64) (its value operand is dead); keep g2 gates
@@ -199,6 +200,11 @@ __device__ __forceinline__ void issue(const Ctx &c, F &&f) {
     }
 }
 
+// column of RA[0:64) where the layer-1 gates of feature chunk ch are parked between C1 and the tangent seeds
+__device__ __forceinline__ int stash_col(int ch) {
+    return 32 * (ch >> 2) + 16 * (ch & 1) + 8 * ((ch >> 1) & 1);
+}
+
 __device__ __forceinline__ float2 as_f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
 // One net of one tile.  NET 0 = a (w1: 12x4 matrix, 48 outputs), NET 1 = b (w2: 2x12 matrix, 24 outputs).
@@ -226,7 +232,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     const uint32_t idesc3 = make_idesc(N3);
     const int h = c.h;
 
-    // ---- L1: layer 1 on CUDA cores -> value operand in RA; gates g1 = 1 - h1^2 stay in registers ----------------------
+    // ---- L1: layer 1 on CUDA cores -> value operand in RA; gates g1 = 1 - h1^2 recomputed from it after the loop ----------
     TRACE(0);
     uint32_t g1[32];
     {
@@ -238,7 +244,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         const float2 ix = make_float2(st.x2, st.x2), iy = make_float2(st.x3, st.x3), iz = make_float2(inz, inz);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int ch = 4 * h + i;
+            const int ch = 2 * i + h;  // interleaved: the thread's four chunks are the ones it reads back below
             uint32_t av[16];
 #pragma unroll
             for (int pq = 0; pq < 8; pq += 2) {
@@ -256,16 +262,31 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     SPLIT(t[e], av[pq + e], av[8 + pq + e]);
-                    g1[8 * i + pq + e] = gate_of(t[e], av[pq + e]);
                 }
             }
             st16(c.ra + 16 * ch, av);
             if (KC >= 1)
                 chunk_issue(c, i, i == 3, [&] {
-                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, i, i == 0);
-                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 4 + i, false);
+                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 2 * i, i == 0);
+                    mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 2 * i + 1, false);
                 });
         }
+    }
+    {
+        // g1 = 1 - h1^2 recomputed from this thread's own operand chunks (hi and lo fp16 pairs) while M1 drains:
+        // 1 - hi^2 - 2 hi lo in packed half arithmetic.  Nothing of it is live during the layer-1 tanh work.
+        const __half2 one2 = __floats2half2_rn(1.0f, 1.0f), m2 = __floats2half2_rn(-2.0f, -2.0f);
+        uint32_t hv[64];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ld16(c.ra + 16 * (2 * j + h), hv + 16 * j);
+        wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int pq = 0; pq < 8; ++pq) {
+                const __half2 hi = bits_h2(hv[16 * j + pq]), lo = bits_h2(hv[16 * j + 8 + pq]);
+                g1[8 * j + pq] = h2_bits(__hfma2(__hmul2(m2, hi), lo, __hfma2(__hneg2(hi), hi, one2)));
+            }
     }
     TRACE(1);
     if (!KC) {
@@ -278,6 +299,13 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     TRACE(4);
 
     // ---- C1: layer-2 value epilogue, in place; g1 parked in RA[0:64) -----------------------------------------------------
+    {
+        // park the gates in RA[0:64) (M1 has completed, M4 will write RA[64:112)).  A thread only overwrites columns it read
+        // itself -- half 0 owns chunks 0,2,4,6 and parks in [0,16),[32,48), half 1 chunks 1,3,5,7 and [16,32),[48,64) -- because
+        // the other thread of the sample may still be before its read-back.
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st8(c.ra + stash_col(2 * j + h), &g1[8 * j]);
+    }
     uint32_t gs[32];
     {
         const float2 *B2P = reinterpret_cast<const float2 *>(sp + SP_B2P);
@@ -301,7 +329,6 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                 }
             }
             st16(c.rd + 16 * ch, av);
-            st8(c.ra + 8 * ch, &g1[8 * i]);
             if (KC >= 1)
                 chunk_issue(c, i, i == 3, [&] {
                     mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, i, i == 0);
@@ -323,7 +350,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     float gz[6];
     uint32_t gst[32];  // the parked layer-1 gates, fetched together with the layer-3 outputs (one TMEM round trip)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ld8(c.ra + 8 * (4 * h + i), gst + 8 * i);
+    for (int i = 0; i < 4; ++i) ld8(c.ra + stash_col(4 * h + i), gst + 8 * i);
     if (NET == 0) {
         // w1 rows 6h .. 6h+5 (columns 24h .. 24h+23): z_r = w1[r,:] . xe, tz, g_z; A0 = g_z w1[r,2], B0 = g_z w1[r,3]
         const float4 xe = error_state(st, ref);
