@@ -40,6 +40,7 @@ struct dp_controller {
     // tensor-core operand images (built by rollout_tc.cu at create time; may be null)
     void *d_tc = nullptr;
     size_t tc_bytes = 0;
+    bool tc_l2_bounded = false;  // layer-2 pre-activations provably small enough for the sign-free tanh (rollout_tc.cu)
     // grow-only device workspace + stream for the *_host entry points
     dp_workspace ws;
     cudaStream_t host_stream = nullptr;

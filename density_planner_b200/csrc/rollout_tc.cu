@@ -220,7 +220,7 @@ __device__ __forceinline__ float4 error_state(const SampleState &st, const float
     return make_float4(st.x0 - r.x, st.x1 - r.y, __fadd_rn(__fsub_rn(st.x2, r.z), st.x4), st.x3 - r.w);
 }
 
-template <int TP, int KC, int TR>
+template <int TP, int KC, int TR, int SG>
 __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const SampleState &st, const float *ref, float (&acc)[4]) {
     const int N3 = NET == 0 ? N3A : N3B;
     const float *sp = c.small + NET * SMALL_NET_FLOATS;
@@ -321,7 +321,8 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                 const float2 y0 = __ffma2_rn(as_f2(d[2 * pq], d[2 * pq + 1]), cs, B2P[8 * ch + pq]);
                 const float2 y1 = __ffma2_rn(as_f2(d[2 * pq + 2], d[2 * pq + 3]), cs, B2P[8 * ch + pq + 1]);
                 float2 t[2];
-                tanh4(y0, y1, t[0], t[1]);
+                if (SG) tanh4_bounded(y0, y1, t[0], t[1]);  // layer-2 pre-activations are bounded by the weights (dp_tc_prepare)
+                else tanh4(y0, y1, t[0], t[1]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     SPLIT(t[e], av[pq + e], av[8 + pq + e]);
@@ -529,7 +530,7 @@ __device__ __forceinline__ void sample_advance(const RolloutParams &p, SampleSta
     st.x3 = __fadd_rn(st.x3, __fmul_rn(u1, dt));
 }
 
-template <int TP, int KC, int BATCH, int TR>
+template <int TP, int KC, int BATCH, int TR, int SG>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -706,7 +707,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
             for (int net = 0; net < 2; ++net) {  // net a, then net b; the two TMEM regions swap roles
                 const uint32_t A = net == 0 ? R0 : R1, Dd = net == 0 ? R1 : R0;
                 c.RA = A; c.RD = Dd; c.ra = A + lane_off; c.rd = Dd + lane_off;
-                chain<TP, KC, TR>(c, ph, net, st, ref, acc);
+                chain<TP, KC, TR, SG>(c, ph, net, st, ref, acc);
             }
             // exchange the partial head sums of the two feature halves (fixed order: both threads get identical totals)
             float *mine = sPart + h * 4 * TILE + c.s;
@@ -746,6 +747,7 @@ int dp_tc_prepare(dp_controller *c, const float *blob) {
     const int off_w2h[2] = {OFF_W2A_HI, OFF_W2B_HI}, off_w2l[2] = {OFF_W2A_LO, OFF_W2B_LO};
     const int off_w3h[2] = {OFF_W3A_HI, OFF_W3B_HI}, off_w3l[2] = {OFF_W3A_LO, OFF_W3B_LO};
     const double k = 2.8853900817779268;  // 2 log2(e)
+    double l2_bound = 0.0;
     for (int m = 0; m < 2; ++m) {
         float *sp = reinterpret_cast<float *>(img.data() + OFF_SMALL) + m * SMALL_NET_FLOATS;
         const float *W1 = p; p += 512;
@@ -763,6 +765,12 @@ int dp_tc_prepare(dp_controller *c, const float *blob) {
         for (int j = 0; j < 128; ++j) sp[SP_B1P + j] = (float)(k * b1[j]);
         build_split_image(p, 128, 128, WSCALE, reinterpret_cast<__half *>(img.data() + off_w2h[m]),
                           reinterpret_cast<__half *>(img.data() + off_w2l[m]));
+        // bound of the scaled layer-2 pre-activation 2 log2(e) (W2 h1 + b2) over |h1| <= 1: row-wise L1 norm
+        for (int r = 0; r < 128; ++r) {
+            double l1 = fabs((double)p[128 * 128 + r]);
+            for (int j = 0; j < 128; ++j) l1 += fabs((double)p[128 * r + j]);
+            if (k * l1 > l2_bound) l2_bound = k * l1;
+        }
         p += 128 * 128;
         for (int j = 0; j < 128; ++j) sp[SP_B2P + j] = (float)(k * p[j]);
         p += 128;
@@ -776,6 +784,10 @@ int dp_tc_prepare(dp_controller *c, const float *blob) {
     DP_CUDA(cudaMalloc(&d, IMAGE_BYTES));
     DP_CUDA(cudaMemcpy(d, img.data(), IMAGE_BYTES, cudaMemcpyHostToDevice));
     c->d_tc = d;
+    // tanh4_bounded shares one reciprocal among four denominators 1 + 2^-y without taking |y|: their product must stay
+    // below 2^126 (the reciprocal must stay a normal number), i.e. every |y| below 31.5 (plus the rounding of the split
+    // operands, far below the margin kept here)
+    c->tc_l2_bounded = l2_bound < 31.4;
     return 0;
 }
 
@@ -789,26 +801,35 @@ int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStr
     static bool attr_set[64] = {};
     static int variant = -1;  // tuning / A-B knob: DP_TC_VARIANT = 100 * K-chunking (0 off, 1 four batches, 2 two) + 10 * tangent products
     typedef void (*kern_t)(RolloutParams);
-    static const kern_t kerns[6] = {rollout_tc_kernel<1, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0>, rollout_tc_kernel<1, 2, 0, 0>,
-                                    rollout_tc_kernel<2, 0, 0, 0>, rollout_tc_kernel<2, 1, 0, 0>, rollout_tc_kernel<2, 2, 0, 0>};
-    static const kern_t kern_batch = rollout_tc_kernel<1, 2, 1, 0>;  // several references per launch (dp_rollout_batch)
-    static const kern_t kern_trace = rollout_tc_kernel<1, 2, 0, 1>;  // with the in-kernel timeline (DP_TC_TRACE)
+    static const kern_t kerns[6] = {rollout_tc_kernel<1, 0, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0, 0>, rollout_tc_kernel<1, 2, 0, 0, 0>,
+                                    rollout_tc_kernel<2, 0, 0, 0, 0>, rollout_tc_kernel<2, 1, 0, 0, 0>, rollout_tc_kernel<2, 2, 0, 0, 0>};
+    // the default variant and the batched one also exist with the sign-free layer-2 tanh (tanh4_bounded); the host picks
+    // them when the weights bound the layer-2 pre-activations (c->tc_l2_bounded, see dp_tc_prepare)
+    static const kern_t kern_bounded = rollout_tc_kernel<1, 2, 0, 0, 1>;
+    static const kern_t kern_batch[2] = {rollout_tc_kernel<1, 2, 1, 0, 0>, rollout_tc_kernel<1, 2, 1, 0, 1>};  // dp_rollout_batch
+    static const kern_t kern_trace = rollout_tc_kernel<1, 2, 0, 1, 0>;  // with the in-kernel timeline (DP_TC_TRACE)
+    static int bounded_ok = -1;  // DP_TC_BOUNDED=0 forces the general tanh (A/B and test knob)
     if (variant < 0) {
         const char *e = getenv("DP_TC_VARIANT");
         const int v = e ? atoi(e) : 210;
         const int kc = (v / 100) % 3, tp = ((v / 10) % 10 == 2) ? 1 : 0;
         variant = 3 * tp + kc;
+        const char *b = getenv("DP_TC_BOUNDED");
+        bounded_ok = (b && atoi(b) == 0) ? 0 : 1;
     }
     if (!attr_set[c->device & 63]) {
         for (int k = 0; k < 6; ++k)
             DP_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        DP_CUDA(cudaFuncSetAttribute(kern_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        DP_CUDA(cudaFuncSetAttribute(kern_bounded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        DP_CUDA(cudaFuncSetAttribute(kern_batch[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        DP_CUDA(cudaFuncSetAttribute(kern_batch[1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         DP_CUDA(cudaFuncSetAttribute(kern_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_set[c->device & 63] = true;
     }
     const bool batch = p.R > 1 || p.T_ref != nullptr;
     const char *trace_path = getenv("DP_TC_TRACE");  // diagnostic: dump an in-kernel clock64 timeline of CTA 0
-    const kern_t kern = batch ? kern_batch : (trace_path ? kern_trace : kerns[variant]);
+    const bool bounded = bounded_ok && c->tc_l2_bounded;
+    const kern_t kern = batch ? kern_batch[bounded] : (trace_path ? kern_trace : (bounded && variant == 2 ? kern_bounded : kerns[variant]));
     RolloutParams q = p;
     q.tc = c->d_tc;
     const long long num_tiles = (p.R > 1 || p.T_ref) ? p.R * ((p.n_per_ref + TILE - 1) / TILE) : (p.N + TILE - 1) / TILE;

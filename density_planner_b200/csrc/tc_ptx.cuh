@@ -169,6 +169,20 @@ __device__ __forceinline__ void tanh4(const float2 yA, const float2 yB, float2 &
     tA = copysign2(__ffma2_rn(two, rA, mone), yA);
     tB = copysign2(__ffma2_rn(two, rB, mone), yB);
 }
+// The same without |y| and without the sign copy, for arguments whose size is bounded: 2^-y may now be large, and the shared
+// reciprocal only works while the product of the four denominators stays a normal number with a normal reciprocal, i.e.
+// every |y| < 31.5 (caller's contract: the host derives the bound from the weights).  tanh x = 2/(1 + 2^-y) - 1.
+__device__ __forceinline__ void tanh4_bounded(const float2 yA, const float2 yB, float2 &tA, float2 &tB) {
+    const float2 one = make_float2(1.0f, 1.0f), two = make_float2(2.0f, 2.0f), mone = make_float2(-1.0f, -1.0f);
+    const float2 aA = __fadd2_rn(make_float2(ex2_approx(-yA.x), ex2_approx(-yA.y)), one);
+    const float2 aB = __fadd2_rn(make_float2(ex2_approx(-yB.x), ex2_approx(-yB.y)), one);
+    const float2 p = __fmul2_rn(aA, aB);
+    const float R = rcp_approx(p.x * p.y);
+    const float2 q = make_float2(R * p.y, R * p.x);
+    const float2 rA = __fmul2_rn(q, aB), rB = __fmul2_rn(q, aA);
+    tA = __ffma2_rn(two, rA, mone);
+    tB = __ffma2_rn(two, rB, mone);
+}
 __device__ __forceinline__ uint32_t h2_bits(const __half2 h) { return *reinterpret_cast<const uint32_t *>(&h); }
 __device__ __forceinline__ __half2 bits_h2(const uint32_t u) { return *reinterpret_cast<const __half2 *>(&u); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) { return h2_bits(__floats2half2_rn(a, b)); }  // a -> low half

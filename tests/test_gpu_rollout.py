@@ -67,6 +67,20 @@ def test_rollout_vs_reference_golden(car, impl, name):
     assert np.abs(margin - g["clip_margin"]).max() < 1e-3
 
 
+@pytest.mark.parametrize("env", [{"DP_TC_BOUNDED": "0"}, {"DP_TC_VARIANT": "110"}, {"DP_TC_VARIANT": "20"}])
+def test_rollout_kernel_variants_vs_reference_golden(env):
+    """The variants the host does not pick by default -- the general tanh (what a controller whose layer-2 weights do not
+    bound the pre-activations gets), four-batch K-chunking, no K-chunking with two tangent products -- against the same golden
+    vectors; one fresh process each because the knobs are read once per process."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "run_rollout_golden.py"), "rollout_n4000_t100", "tc"],
+                       env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 def test_rollout_host_buffers_and_strided_store(car, impl):
     """CPU tensors in / CPU tensors out (dp_rollout_host), and stride>1 equals subsampling of stride 1."""
