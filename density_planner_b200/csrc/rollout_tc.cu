@@ -69,7 +69,8 @@ constexpr int SP_B2P = 640;  // [128] b2 * 2 log2(e)
 constexpr int SP_B3 = 768;   // [64]
 constexpr int SP_C0H = 832;  // [64] half2 pairs of W1[:,0]  (tangent seed d/dtheta)
 constexpr int SP_C1H = 896;  // [64] half2 pairs of W1[:,1]  (tangent seed d/dv)
-static_assert(SP_C1H + 64 == SMALL_NET_FLOATS, "small block layout");
+constexpr int SP_B3R = 960;  // [64] b3 - rowsum(W3): the layer-3 bias when layer 3 is fed r = (1 + h2) / 2 (SG kernels)
+static_assert(SP_B3R + 64 == SMALL_NET_FLOATS, "small block layout");
 
 // shared memory behind the image
 constexpr int OFF_Z = IMAGE_BYTES;                              // float [2 groups][36][128]: tz, A, B per z-row
@@ -321,12 +322,19 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                 const float2 y0 = __ffma2_rn(as_f2(d[2 * pq], d[2 * pq + 1]), cs, B2P[8 * ch + pq]);
                 const float2 y1 = __ffma2_rn(as_f2(d[2 * pq + 2], d[2 * pq + 3]), cs, B2P[8 * ch + pq + 1]);
                 float2 t[2];
-                if (SG) tanh4_bounded(y0, y1, t[0], t[1]);  // layer-2 pre-activations are bounded by the weights (dp_tc_prepare)
+                // SG: the layer-2 pre-activations are bounded by the weights (dp_tc_prepare), so no |y| / sign copy is
+                // needed, and layer 3 takes r = (1 + h2) / 2 as its operand (scale and bias adjusted in R4, gate = g2 / 4
+                // made up for in R56)
+                if (SG) sigm4_bounded(y0, y1, t[0], t[1]);
                 else tanh4(y0, y1, t[0], t[1]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     SPLIT(t[e], av[pq + e], av[8 + pq + e]);
-                    gs[8 * i + pq + e] = gate_of(t[e], av[pq + e]);
+                    if (SG) {
+                        const float2 g = __ffma2_rn(make_float2(-t[e].x, -t[e].y), t[e], t[e]);  // r (1 - r)
+                        gs[8 * i + pq + e] = pack_h2(g.x, g.y);
+                    } else
+                        gs[8 * i + pq + e] = gate_of(t[e], av[pq + e]);
                 }
             }
             st16(c.rd + 16 * ch, av);
@@ -347,7 +355,9 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     TRACE(7);
 
     // ---- R4: layer-3 value outputs -------------------------------------------------------------------------------------------
-    const float *b3 = sp + SP_B3;
+    const float *b3 = sp + (SG ? SP_B3R : SP_B3);
+    constexpr float OSCALE = SG ? 2.0f * INV_WSCALE : INV_WSCALE;   // accumulator -> layer-3 output
+    constexpr float TSCALE = SG ? 4.0f * INV_S2 : INV_S2;            // accumulator -> layer-3 tangent
     float gz[6];
     uint32_t gst[32];  // the parked layer-1 gates, fetched together with the layer-3 outputs (one TMEM round trip)
 #pragma unroll
@@ -364,10 +374,10 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         for (int rr = 0; rr < 6; ++rr) {
             const int r = 6 * h + rr;
             const float4 bb = *reinterpret_cast<const float4 *>(b3 + 4 * r);
-            const float w0 = fmaf(__uint_as_float(v[4 * rr + 0]), INV_WSCALE, bb.x);
-            const float w1 = fmaf(__uint_as_float(v[4 * rr + 1]), INV_WSCALE, bb.y);
-            const float w2 = fmaf(__uint_as_float(v[4 * rr + 2]), INV_WSCALE, bb.z);
-            const float w3 = fmaf(__uint_as_float(v[4 * rr + 3]), INV_WSCALE, bb.w);
+            const float w0 = fmaf(__uint_as_float(v[4 * rr + 0]), OSCALE, bb.x);
+            const float w1 = fmaf(__uint_as_float(v[4 * rr + 1]), OSCALE, bb.y);
+            const float w2 = fmaf(__uint_as_float(v[4 * rr + 2]), OSCALE, bb.z);
+            const float w3 = fmaf(__uint_as_float(v[4 * rr + 3]), OSCALE, bb.w);
             float z = w0 * xe.x;
             z = fmaf(w1, xe.y, z);
             z = fmaf(w2, xe.z, z);
@@ -389,7 +399,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
             const int r = 6 * h + rr;
             const float d0 = __uint_as_float(h ? v[6 + rr] : v[rr]);
             const float d1 = __uint_as_float(h ? v[18 + rr] : v[12 + rr]);
-            const float w20 = fmaf(d0, INV_WSCALE, b3[r]), w21 = fmaf(d1, INV_WSCALE, b3[12 + r]);
+            const float w20 = fmaf(d0, OSCALE, b3[r]), w21 = fmaf(d1, OSCALE, b3[12 + r]);
             const float tz = c.sZ[(0 * 12 + r) * TILE + c.s];
             acc[0] = fmaf(w20, tz, acc[0]);
             acc[1] = fmaf(w21, tz, acc[1]);
@@ -484,7 +494,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
             dzv = fmaf(__uint_as_float(b[4 * rr + 1]), xe.y, dzv);
             dzv = fmaf(__uint_as_float(b[4 * rr + 2]), xe.z, dzv);
             dzv = fmaf(__uint_as_float(b[4 * rr + 3]), xe.w, dzv);
-            const float gi = gz[rr] * INV_S2;
+            const float gi = gz[rr] * TSCALE;
             c.sZ[(1 * 12 + r) * TILE + c.s] = fmaf(gi, dzt, c.sZ[(1 * 12 + r) * TILE + c.s]);
             c.sZ[(2 * 12 + r) * TILE + c.s] = fmaf(gi, dzv, c.sZ[(2 * 12 + r) * TILE + c.s]);
         }
@@ -497,8 +507,8 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
 #pragma unroll
         for (int rr = 0; rr < 6; ++rr) {
             const int r = 6 * h + rr;
-            const float dt0 = __uint_as_float(h ? a[6 + rr] : a[rr]) * INV_S2;
-            const float dv1 = __uint_as_float(h ? b[10 + rr] : b[4 + rr]) * INV_S2;
+            const float dt0 = __uint_as_float(h ? a[6 + rr] : a[rr]) * TSCALE;
+            const float dv1 = __uint_as_float(h ? b[10 + rr] : b[4 + rr]) * TSCALE;
             const float tz = c.sZ[(0 * 12 + r) * TILE + c.s];
             acc[2] = fmaf(dt0, tz, acc[2]);
             acc[3] = fmaf(dv1, tz, acc[3]);
@@ -776,6 +786,8 @@ int dp_tc_prepare(dp_controller *c, const float *blob) {
         p += 128;
         build_split_image(p, nouts[m], nrows3[m], WSCALE, reinterpret_cast<__half *>(img.data() + off_w3h[m]),
                           reinterpret_cast<__half *>(img.data() + off_w3l[m]));
+        for (int r = 0; r < nouts[m]; ++r)
+            sp[SP_B3R + r] = (float)((double)p[nouts[m] * 128 + r] - split_image_rowsum(p, r, WSCALE) / (double)WSCALE);
         p += nouts[m] * 128;
         memcpy(sp + SP_B3, p, sizeof(float) * nouts[m]);
         p += nouts[m];

@@ -23,8 +23,8 @@ constexpr int OFF_W3A_HI = OFF_W2B_LO + W2_BYTES;
 constexpr int OFF_W3A_LO = OFF_W3A_HI + W3A_BYTES;
 constexpr int OFF_W3B_HI = OFF_W3A_LO + W3A_BYTES;
 constexpr int OFF_W3B_LO = OFF_W3B_HI + W3B_BYTES;
-constexpr int OFF_SMALL = OFF_W3B_LO + W3B_BYTES;  // per-net fp32 block (layout owned by each kernel), 960 floats per net
-constexpr int SMALL_NET_FLOATS = 960;
+constexpr int OFF_SMALL = OFF_W3B_LO + W3B_BYTES;  // per-net fp32 block (layout owned by each kernel), 1024 floats per net
+constexpr int SMALL_NET_FLOATS = 1024;
 constexpr int IMAGE_BYTES = OFF_SMALL + 2 * SMALL_NET_FLOATS * 4;
 static_assert(IMAGE_BYTES % 16 == 0, "image copied with 16-byte vectors");
 
@@ -183,6 +183,19 @@ __device__ __forceinline__ void tanh4_bounded(const float2 yA, const float2 yB, 
     tA = __ffma2_rn(two, rA, mone);
     tB = __ffma2_rn(two, rB, mone);
 }
+// ... and the variant that returns r = 1 / (1 + 2^-y) = (1 + tanh x) / 2 itself: a layer whose consumer is linear can take
+// r as its operand (W tanh = 2 W r - W 1: the factor and the row sums go into the consumer's scale and bias), which saves
+// the 2 r - 1 step; the gate is 1 - tanh^2 = 4 r (1 - r).
+__device__ __forceinline__ void sigm4_bounded(const float2 yA, const float2 yB, float2 &rA, float2 &rB) {
+    const float2 one = make_float2(1.0f, 1.0f);
+    const float2 aA = __fadd2_rn(make_float2(ex2_approx(-yA.x), ex2_approx(-yA.y)), one);
+    const float2 aB = __fadd2_rn(make_float2(ex2_approx(-yB.x), ex2_approx(-yB.y)), one);
+    const float2 p = __fmul2_rn(aA, aB);
+    const float R = rcp_approx(p.x * p.y);
+    const float2 q = make_float2(R * p.y, R * p.x);
+    rA = __fmul2_rn(q, aB);
+    rB = __fmul2_rn(q, aA);
+}
 __device__ __forceinline__ uint32_t h2_bits(const __half2 h) { return *reinterpret_cast<const uint32_t *>(&h); }
 __device__ __forceinline__ __half2 bits_h2(const uint32_t u) { return *reinterpret_cast<const __half2 *>(&u); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) { return h2_bits(__floats2half2_rn(a, b)); }  // a -> low half
@@ -225,6 +238,18 @@ __device__ __forceinline__ uint32_t gate_of(const float2 t, const uint32_t hi) {
 
 // ---- host: canonical no-swizzle K-major image of W [n_rows][128] (rows >= n_valid are zero) --------------------------------
 inline size_t canon_index(int r, int k) { return ((size_t)(r / 8) * 16 + (k / 8)) * 64 + (r % 8) * 8 + (k % 8); }
+
+// sum over k of the row's split image (hi + lo), i.e. what an all-ones operand would accumulate
+inline double split_image_rowsum(const float *W, int r, float scale) {
+    double s = 0.0;
+    for (int k = 0; k < 128; ++k) {
+        const float w = W[(size_t)r * 128 + k] * scale;
+        const __half h = __float2half_rn(w);
+        const __half l = __float2half_rn(w - __half2float(h));
+        s += (double)__half2float(h) + (double)__half2float(l);
+    }
+    return s;
+}
 
 inline void build_split_image(const float *W, int n_valid, int n_rows, float scale, __half *hi, __half *lo) {
     for (int r = 0; r < n_rows; ++r)
