@@ -18,7 +18,7 @@
 //     one group waits for its MMAs the other group's epilogue math fills the issue slots, and vice versa.
 //   * no MMA warp: after the group's named barrier, one elected thread of the group's first warp issues the group's
 //     tcgen05.mma batch and commits it to the group's mbarrier; everybody in the group then waits on that mbarrier.
-//     M1, M4 and M2 are K-CHUNKED: in iteration i of the producing loop the other warps only ARRIVE on a chunk barrier
+//     M1 and M4 are K-CHUNKED: in iteration i of the producing loop the other warps only ARRIVE on a chunk barrier
 //     and go on, the first warp waits for them and issues the K-chunks completed there: the tensor pipe works through a batch
 //     while the CUDA cores are still producing the rest of its operand.
 //   * chain for one (tile, net), RA / RD = the group's two regions (they swap roles from one chain to the next):
@@ -28,7 +28,8 @@
 //       C1    per 16-feature chunk: drain RD, h2 = tanh(.), write h2 hi/lo IN PLACE of the drained accumulator chunk
 //             (RD becomes the layer-3 value operand); park g1 in RA[0:64) (its value operand is dead); keep g2 gates
 //       M4    layer-3 value outputs (48 / 32 cols)                  RD -> RA[64:112)
-//       R4    read the value outputs (controller matrices); tangent seeds g1*W1[:,theta], g1*W1[:,v] -> RD[0:64), RD[64:128)
+//       R4    read the value outputs (controller matrices) into registers; tangent seeds g1*W1[:,theta], g1*W1[:,v] ->
+//             RD[0:64), RD[64:128) from the parked gates; the value-output math itself runs after the M2 issue, in its shadow
 //       M2    d/dtheta through layer 2                              RD[0:64)   -> RA (128 cols)
 //       C2    drain RA, scale by g2 -> RD[0:64) in place of the seed
 //       M3/C3 the same for d/dv                                     RD[64:128) -> RA -> RD[64:128)
@@ -59,7 +60,7 @@ constexpr int GT = GW * 32;       // threads per group
 constexpr int NGROUPS = 2;
 constexpr int NTHREADS = NGROUPS * GT;
 // kernel variants (template parameters): TP = tangent products (2: fp16 tangent activations x (hi + lo) weights; 1: hi
-// weights only, the default), KC = K-chunked MMA issue (0 off, 1 for M1, M4 and M2, 2 for M1 and M4 only: the default), BATCH = several references
+// weights only, the default), KC = K-chunked MMA issue of M1 and M4 (0 off, 1 on: the default), BATCH = several references
 // per launch (dp_rollout_batch), TR = in-kernel clock64 timeline (DP_TC_TRACE)
 
 // per-net fp32 block of the operand image (this kernel's own layout of the "small" section)
@@ -266,7 +267,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                 }
             }
             st16(c.ra + 16 * ch, av);
-            if (KC >= 1)
+            if (KC)
                 chunk_issue(c, i, i == 3, [&] {
                     mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 2 * i, i == 0);
                     mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 2 * i + 1, false);
@@ -338,7 +339,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                 }
             }
             st16(c.rd + 16 * ch, av);
-            if (KC >= 1)
+            if (KC)
                 chunk_issue(c, i, i == 3, [&] {
                     mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, i, i == 0);
                     mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, 4 + i, false);
@@ -359,17 +360,48 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     constexpr float OSCALE = SG ? 2.0f * INV_WSCALE : INV_WSCALE;   // accumulator -> layer-3 output
     constexpr float TSCALE = SG ? 4.0f * INV_S2 : INV_S2;            // accumulator -> layer-3 tangent
     float gz[6];
-    uint32_t gst[32];  // the parked layer-1 gates, fetched together with the layer-3 outputs (one TMEM round trip)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) ld8(c.ra + stash_col(4 * h + i), gst + 8 * i);
+    // Order: (1) fetch the layer-3 outputs (24 columns) into registers, (2) build the tangent seeds chunk by chunk from the
+    // parked gates (double-buffered 8-column reads, so only 16 gate registers are live), (3) issue M2, (4) do the
+    // value-output math (z rows, tanh, head sums) in M2's shadow.
+    uint32_t v[24];
     if (NET == 0) {
-        // w1 rows 6h .. 6h+5 (columns 24h .. 24h+23): z_r = w1[r,:] . xe, tz, g_z; A0 = g_z w1[r,2], B0 = g_z w1[r,3]
-        const float4 xe = error_state(st, ref);
-        uint32_t v[24];
         ld8(c.ra + 64 + 24 * h, v);
         ld8(c.ra + 64 + 24 * h + 8, v + 8);
         ld8(c.ra + 64 + 24 * h + 16, v + 16);
+    } else {
+        ld16(c.ra + 64, v);
+        ld8(c.ra + 64 + 16, v + 16);
+    }
+    {
+        const uint32_t *c0h = reinterpret_cast<const uint32_t *>(sp + SP_C0H), *c1h = reinterpret_cast<const uint32_t *>(sp + SP_C1H);
+        uint32_t gb[2][8];
+        ld8(c.ra + stash_col(4 * h), gb[0]);
         wait_ld();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ch = 4 * h + i;
+            if (i < 3) ld8(c.ra + stash_col(ch + 1), gb[(i + 1) & 1]);
+            uint32_t at0[8], at1[8], k0[8], k1[8];
+            *reinterpret_cast<uint4 *>(k0) = *reinterpret_cast<const uint4 *>(c0h + 8 * ch);
+            *reinterpret_cast<uint4 *>(k0 + 4) = *reinterpret_cast<const uint4 *>(c0h + 8 * ch + 4);
+            *reinterpret_cast<uint4 *>(k1) = *reinterpret_cast<const uint4 *>(c1h + 8 * ch);
+            *reinterpret_cast<uint4 *>(k1 + 4) = *reinterpret_cast<const uint4 *>(c1h + 8 * ch + 4);
+#pragma unroll
+            for (int pq = 0; pq < 8; ++pq) {
+                at0[pq] = h2_bits(__hmul2(bits_h2(gb[i & 1][pq]), bits_h2(k0[pq])));
+                at1[pq] = h2_bits(__hmul2(bits_h2(gb[i & 1][pq]), bits_h2(k1[pq])));
+            }
+            st8(c.rd + 8 * ch, at0);
+            st8(c.rd + 64 + 8 * ch, at1);
+            if (i < 3) wait_ld();
+        }
+    }
+    TRACE(8);
+    publish(c);  // every read of RA (outputs, parked gates) of this thread has completed
+    issue(c, [&] { mma_tangent<TP>(c.RA, c.RD, w2h, w2l, idesc128); });
+    TRACE(9);
+    if (NET == 0) {
+        const float4 xe = error_state(st, ref);
 #pragma unroll
         for (int rr = 0; rr < 6; ++rr) {
             const int r = 6 * h + rr;
@@ -389,11 +421,6 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
             c.sZ[(2 * 12 + r) * TILE + c.s] = gz[rr] * w3;  // + d xe3 / d v * w1[r][3]
         }
     } else {
-        // w2[0][r], w2[1][r] (columns r, 12 + r) for rows 6h .. 6h+5
-        uint32_t v[24];
-        ld16(c.ra + 64, v);
-        ld8(c.ra + 64 + 16, v + 16);
-        wait_ld();
 #pragma unroll
         for (int rr = 0; rr < 6; ++rr) {
             const int r = 6 * h + rr;
@@ -407,37 +434,6 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
             acc[3] = fmaf(w21, c.sZ[(2 * 12 + r) * TILE + c.s], acc[3]);
         }
     }
-    // ---- tangent seeds g1 * W1[:,theta], g1 * W1[:,v] -> RD (the layer-3 value operand is dead) ---------------------------------
-    {
-        const uint32_t *c0h = reinterpret_cast<const uint32_t *>(sp + SP_C0H), *c1h = reinterpret_cast<const uint32_t *>(sp + SP_C1H);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int ch = 4 * h + i;
-            uint32_t at0[8], at1[8], k0[8], k1[8];
-            *reinterpret_cast<uint4 *>(k0) = *reinterpret_cast<const uint4 *>(c0h + 8 * ch);
-            *reinterpret_cast<uint4 *>(k0 + 4) = *reinterpret_cast<const uint4 *>(c0h + 8 * ch + 4);
-            *reinterpret_cast<uint4 *>(k1) = *reinterpret_cast<const uint4 *>(c1h + 8 * ch);
-            *reinterpret_cast<uint4 *>(k1 + 4) = *reinterpret_cast<const uint4 *>(c1h + 8 * ch + 4);
-#pragma unroll
-            for (int pq = 0; pq < 8; ++pq) {
-                at0[pq] = h2_bits(__hmul2(bits_h2(gst[8 * i + pq]), bits_h2(k0[pq])));
-                at1[pq] = h2_bits(__hmul2(bits_h2(gst[8 * i + pq]), bits_h2(k1[pq])));
-            }
-            st8(c.rd + 8 * ch, at0);
-            st8(c.rd + 64 + 8 * ch, at1);
-            if (KC == 1)  // every thread reaches its first arrival after all its reads of RA (outputs, parked gates) completed
-                chunk_issue(c, i, i == 3, [&] {
-                    mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, i, i == 0);
-                    mma_tangent_k<TP>(c.RA, c.RD, w2h, w2l, idesc128, 4 + i, false);
-                });
-        }
-    }
-    TRACE(8);
-    if (KC != 1) {  // KC == 2: M2 (eight short MMAs) in one batch, without the four chunk barriers
-        publish(c);
-        issue(c, [&] { mma_tangent<TP>(c.RA, c.RD, w2h, w2l, idesc128); });
-    }
-    TRACE(9);
     await(c, ph);
     TRACE(10);
 
@@ -811,26 +807,26 @@ void dp_tc_release(dp_controller *c) {
 int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStream_t stream) {
     DP_REQUIRE(c->d_tc != nullptr, "DP_IMPL_TC: tensor-core weight image missing");
     static bool attr_set[64] = {};
-    static int variant = -1;  // tuning / A-B knob: DP_TC_VARIANT = 100 * K-chunking (0 off, 1 four batches, 2 two) + 10 * tangent products
+    static int variant = -1;  // tuning / A-B knob: DP_TC_VARIANT = 100 * K-chunking (0 off, 1 on) + 10 * tangent products
     typedef void (*kern_t)(RolloutParams);
-    static const kern_t kerns[6] = {rollout_tc_kernel<1, 0, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0, 0>, rollout_tc_kernel<1, 2, 0, 0, 0>,
-                                    rollout_tc_kernel<2, 0, 0, 0, 0>, rollout_tc_kernel<2, 1, 0, 0, 0>, rollout_tc_kernel<2, 2, 0, 0, 0>};
+    static const kern_t kerns[4] = {rollout_tc_kernel<1, 0, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0, 0>,
+                                    rollout_tc_kernel<2, 0, 0, 0, 0>, rollout_tc_kernel<2, 1, 0, 0, 0>};
     // the default variant and the batched one also exist with the sign-free layer-2 tanh (tanh4_bounded); the host picks
     // them when the weights bound the layer-2 pre-activations (c->tc_l2_bounded, see dp_tc_prepare)
-    static const kern_t kern_bounded = rollout_tc_kernel<1, 2, 0, 0, 1>;
-    static const kern_t kern_batch[2] = {rollout_tc_kernel<1, 2, 1, 0, 0>, rollout_tc_kernel<1, 2, 1, 0, 1>};  // dp_rollout_batch
-    static const kern_t kern_trace = rollout_tc_kernel<1, 2, 0, 1, 0>;  // with the in-kernel timeline (DP_TC_TRACE)
+    static const kern_t kern_bounded = rollout_tc_kernel<1, 1, 0, 0, 1>;
+    static const kern_t kern_batch[2] = {rollout_tc_kernel<1, 1, 1, 0, 0>, rollout_tc_kernel<1, 1, 1, 0, 1>};  // dp_rollout_batch
+    static const kern_t kern_trace = rollout_tc_kernel<1, 1, 0, 1, 0>;  // with the in-kernel timeline (DP_TC_TRACE)
     static int bounded_ok = -1;  // DP_TC_BOUNDED=0 forces the general tanh (A/B and test knob)
     if (variant < 0) {
         const char *e = getenv("DP_TC_VARIANT");
-        const int v = e ? atoi(e) : 210;
-        const int kc = (v / 100) % 3, tp = ((v / 10) % 10 == 2) ? 1 : 0;
-        variant = 3 * tp + kc;
+        const int v = e ? atoi(e) : 110;
+        const int kc = (v / 100) ? 1 : 0, tp = ((v / 10) % 10 == 2) ? 1 : 0;
+        variant = 2 * tp + kc;
         const char *b = getenv("DP_TC_BOUNDED");
         bounded_ok = (b && atoi(b) == 0) ? 0 : 1;
     }
     if (!attr_set[c->device & 63]) {
-        for (int k = 0; k < 6; ++k)
+        for (int k = 0; k < 4; ++k)
             DP_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         DP_CUDA(cudaFuncSetAttribute(kern_bounded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         DP_CUDA(cudaFuncSetAttribute(kern_batch[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -841,7 +837,7 @@ int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStr
     const bool batch = p.R > 1 || p.T_ref != nullptr;
     const char *trace_path = getenv("DP_TC_TRACE");  // diagnostic: dump an in-kernel clock64 timeline of CTA 0
     const bool bounded = bounded_ok && c->tc_l2_bounded;
-    const kern_t kern = batch ? kern_batch[bounded] : (trace_path ? kern_trace : (bounded && variant == 2 ? kern_bounded : kerns[variant]));
+    const kern_t kern = batch ? kern_batch[bounded] : (trace_path ? kern_trace : (bounded && variant == 1 ? kern_bounded : kerns[variant]));
     RolloutParams q = p;
     q.tc = c->d_tc;
     const long long num_tiles = (p.R > 1 || p.T_ref) ? p.R * ((p.n_per_ref + TILE - 1) / TILE) : (p.N + TILE - 1) / TILE;

@@ -67,10 +67,10 @@ def test_rollout_vs_reference_golden(car, impl, name):
     assert np.abs(margin - g["clip_margin"]).max() < 1e-3
 
 
-@pytest.mark.parametrize("env", [{"DP_TC_BOUNDED": "0"}, {"DP_TC_VARIANT": "110"}, {"DP_TC_VARIANT": "20"}])
+@pytest.mark.parametrize("env", [{"DP_TC_BOUNDED": "0"}, {"DP_TC_VARIANT": "120"}, {"DP_TC_VARIANT": "20"}])
 def test_rollout_kernel_variants_vs_reference_golden(env):
     """The variants the host does not pick by default -- the general tanh (what a controller whose layer-2 weights do not
-    bound the pre-activations gets), four-batch K-chunking, no K-chunking with two tangent products -- against the same golden
+    bound the pre-activations gets), two tangent products with and without K-chunked MMA issue -- against the same golden
     vectors; one fresh process each because the knobs are read once per process."""
     import os
     import subprocess
