@@ -574,7 +574,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
     const uint32_t tm = *tmem_ptr_s;
 
     Ctx c;
-    const uint32_t R0 = tm + 256u * grp, R1 = R0 + 128u, lane_off = (uint32_t)(32 * q) << 16;
+    // warp-uniform TMEM addresses: passing them through redux.sync tells the compiler so (the result lives in a uniform
+    // register), and tcgen05.ld / st / mma take their addresses from uniform registers without a per-use R2UR
+    const uint32_t R0 = __reduce_max_sync(0xffffffffu, tm + 256u * grp), R1 = R0 + 128u;
+    const uint32_t lane_off = __reduce_max_sync(0xffffffffu, (uint32_t)(32 * q) << 16);
     c.bar = smem_u32(bars + grp);
     c.sbase = smem_u32(smem);
     c.bar_id = 1 + grp;
