@@ -59,6 +59,12 @@ constexpr int GW = 8;             // warps per group
 constexpr int GT = GW * 32;       // threads per group
 constexpr int NGROUPS = 2;
 constexpr int NTHREADS = NGROUPS * GT;
+// which warp of the group issues which MMA batch (a batch and its commit always come from the same thread)
+#ifndef DP_ISSUERS
+#define DP_ISSUERS 100000   // 1 followed by the warp (0..7) for M1, M4, M2, M3, M5+M6
+#endif
+constexpr int ISSUER_M1 = DP_ISSUERS / 10000 % 10, ISSUER_M4 = DP_ISSUERS / 1000 % 10, ISSUER_M2 = DP_ISSUERS / 100 % 10,
+              ISSUER_M3 = DP_ISSUERS / 10 % 10, ISSUER_M56 = DP_ISSUERS % 10;
 // kernel variants (template parameters): TP = tangent products (2: fp16 tangent activations x (hi + lo) weights; 1: hi
 // weights only, the default), KC = K-chunked MMA issue of M1 and M4 (0 off, 1 on: the default), BATCH = several references
 // per launch (dp_rollout_batch), TR = in-kernel clock64 timeline (DP_TC_TRACE)
@@ -113,7 +119,7 @@ struct Ctx {
     int bar_id;         // the group's named barrier
     int h;              // feature half of this thread
     int s;              // sample within the tile
-    bool leader;        // first warp of the group: issues the MMAs
+    int wl;             // warp within the group; the MMA batches are issued by warp ISSUER_* of the group (one per site)
     const float *small; // fp32 blocks of both nets
     float *sZ;          // this group's [36][128]
     const float4 *sCB;  // this group's [2 nets][64 pairs] {wz pair, per-step constant pair} (see the step loop)
@@ -173,11 +179,11 @@ __device__ __forceinline__ void mma_tangent_k(uint32_t d, uint32_t a0, uint64_t 
 // chunk's named barrier and carry on with the next chunk; the leader warp waits for them and issues the MMAs of those
 // two K-chunks, so the tensor pipe works through the batch while the CUDA cores are still producing the rest of it.
 template <typename F>
-__device__ __forceinline__ void chunk_issue(const Ctx &c, int i, bool last, F &&f) {
+__device__ __forceinline__ void chunk_issue(const Ctx &c, int who, int i, bool last, F &&f) {
     wait_st();
     fence_before();
     const int id = 5 + 4 * c.grp + i;
-    if (c.leader) {
+    if (c.wl == who) {
         asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GT) : "memory");
         fence_after();
         if (elect_one()) {
@@ -191,8 +197,8 @@ __device__ __forceinline__ void chunk_issue(const Ctx &c, int i, bool last, F &&
 }
 
 template <typename F>
-__device__ __forceinline__ void issue(const Ctx &c, F &&f) {
-    if (c.leader) {
+__device__ __forceinline__ void issue(const Ctx &c, int who, F &&f) {
+    if (c.wl == who) {
         fence_after();
         if (elect_one()) {
             f();
@@ -268,7 +274,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
             }
             st16(c.ra + 16 * ch, av);
             if (KC)
-                chunk_issue(c, i, i == 3, [&] {
+                chunk_issue(c, ISSUER_M1, i, i == 3, [&] {
                     mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 2 * i, i == 0);
                     mma_value_k(c.RD, c.RA, w2h, w2l, idesc128, 2 * i + 1, false);
                 });
@@ -294,7 +300,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     if (!KC) {
         publish(c);
         TRACE(2);
-        issue(c, [&] { mma_value(c.RD, c.RA, w2h, w2l, idesc128); });
+        issue(c, ISSUER_M1, [&] { mma_value(c.RD, c.RA, w2h, w2l, idesc128); });
     }
     TRACE(3);
     await(c, ph);
@@ -340,7 +346,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
             }
             st16(c.rd + 16 * ch, av);
             if (KC)
-                chunk_issue(c, i, i == 3, [&] {
+                chunk_issue(c, ISSUER_M4, i, i == 3, [&] {
                     mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, i, i == 0);
                     mma_value_k(c.RA + 64, c.RD, w3h, w3l, idesc3, 4 + i, false);
                 });
@@ -349,7 +355,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     TRACE(5);
     if (!KC) {
         publish(c);
-        issue(c, [&] { mma_value(c.RA + 64, c.RD, w3h, w3l, idesc3); });
+        issue(c, ISSUER_M4, [&] { mma_value(c.RA + 64, c.RD, w3h, w3l, idesc3); });
     }
     TRACE(6);
     await(c, ph);
@@ -369,8 +375,8 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         ld8(c.ra + 64 + 24 * h + 8, v + 8);
         ld8(c.ra + 64 + 24 * h + 16, v + 16);
     } else {
-        ld16(c.ra + 64, v);
-        ld8(c.ra + 64 + 16, v + 16);
+        ld8(c.ra + 64 + 6 * h, v);            // w2[0][6h .. 6h+5] (two spare columns)
+        ld8(c.ra + 64 + 12 + 6 * h, v + 8);   // w2[1][6h .. 6h+5]
     }
     {
         const uint32_t *c0h = reinterpret_cast<const uint32_t *>(sp + SP_C0H), *c1h = reinterpret_cast<const uint32_t *>(sp + SP_C1H);
@@ -398,7 +404,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     }
     TRACE(8);
     publish(c);  // every read of RA (outputs, parked gates) of this thread has completed
-    issue(c, [&] { mma_tangent<TP>(c.RA, c.RD, w2h, w2l, idesc128); });
+    issue(c, ISSUER_M2, [&] { mma_tangent<TP>(c.RA, c.RD, w2h, w2l, idesc128); });
     TRACE(9);
     if (NET == 0) {
         const float4 xe = error_state(st, ref);
@@ -424,8 +430,8 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
 #pragma unroll
         for (int rr = 0; rr < 6; ++rr) {
             const int r = 6 * h + rr;
-            const float d0 = __uint_as_float(h ? v[6 + rr] : v[rr]);
-            const float d1 = __uint_as_float(h ? v[18 + rr] : v[12 + rr]);
+            const float d0 = __uint_as_float(v[rr]);
+            const float d1 = __uint_as_float(v[8 + rr]);
             const float w20 = fmaf(d0, OSCALE, b3[r]), w21 = fmaf(d1, OSCALE, b3[12 + r]);
             const float tz = c.sZ[(0 * 12 + r) * TILE + c.s];
             acc[0] = fmaf(w20, tz, acc[0]);
@@ -457,9 +463,9 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         TRACE(11 + 2 * k);
         publish(c);
         if (k == 0) {
-            issue(c, [&] { mma_tangent<TP>(c.RA, c.RD + 64, w2h, w2l, idesc128); });
+            issue(c, ISSUER_M3, [&] { mma_tangent<TP>(c.RA, c.RD + 64, w2h, w2l, idesc128); });
         } else {
-            issue(c, [&] {
+            issue(c, ISSUER_M56, [&] {
                 mma_tangent<TP>(c.RA, c.RD, w3h, w3l, idesc3);
                 mma_tangent<TP>(c.RA + N3, c.RD + 64, w3h, w3l, idesc3);
             });
@@ -496,15 +502,15 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         }
     } else {
         // d w2[0][r] / d theta = theta accumulator column r; d w2[1][r] / d v = v accumulator column 12 + r
-        uint32_t a[16], b[16];
-        ld16(c.ra, a);
-        ld16(c.ra + N3 + 8, b);  // v accumulator columns 8 .. 23
+        uint32_t a[8], b[8];
+        ld8(c.ra + 6 * h, a);
+        ld8(c.ra + N3 + 12 + 6 * h, b);
         wait_ld();
 #pragma unroll
         for (int rr = 0; rr < 6; ++rr) {
             const int r = 6 * h + rr;
-            const float dt0 = __uint_as_float(h ? a[6 + rr] : a[rr]) * TSCALE;
-            const float dv1 = __uint_as_float(h ? b[10 + rr] : b[4 + rr]) * TSCALE;
+            const float dt0 = __uint_as_float(a[rr]) * TSCALE;
+            const float dv1 = __uint_as_float(b[rr]) * TSCALE;
             const float tz = c.sZ[(0 * 12 + r) * TILE + c.s];
             acc[2] = fmaf(dt0, tz, acc[2]);
             acc[3] = fmaf(dv1, tz, acc[3]);
@@ -583,7 +589,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
     c.bar_id = 1 + grp;
     c.h = h;
     c.s = 32 * q + lane;
-    c.leader = wl == 0;
+    c.wl = wl;
     c.small = reinterpret_cast<const float *>(smem + OFF_SMALL);
     c.sZ = reinterpret_cast<float *>(smem + OFF_Z) + grp * 36 * TILE;
     c.sCB = reinterpret_cast<const float4 *>(smem + OFF_CB) + grp * 2 * 64;

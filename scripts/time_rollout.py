@@ -5,6 +5,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import density_planner_b200 as dp
+if os.environ.get("DP_LIB_VARIANT"):  # development: a variant build made by scripts/build_variant.sh
+    import density_planner_b200._lib as _lib
+    _lib.LIB_PATH = os.path.join(ROOT, "build", "variants", os.environ["DP_LIB_VARIANT"] + ".so")
 impl = sys.argv[1]
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 100
