@@ -152,11 +152,23 @@ int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const
     const int nd = (flags & DP_XY_ONLY) ? 2 : 5;
     // Samples are processed in chunks of two whole waves (one wave = 2 tiles of 128 samples per SM); the device->host copy
     // of chunk k overlaps the rollout of chunk k+1 (two output buffers, a compute stream and a copy stream).  Small chunks
-    // keep the exposed tail (the last chunk's copy) short: ~13 chunks for 1M samples.
+    // keep the exposed tail (the last chunk's copy) short: ~14 chunks for 1M samples.
     const int64_t wave = 2 * 128LL * c->num_sms;
     int64_t chunk = 2 * wave;
     if (chunk > N) chunk = N;
-    const int64_t nchunks = (N + chunk - 1) / chunk;
+    // the first chunk is a single wave, so that the copy engine starts after one wave instead of two, and what is left at
+    // the end is split so that the last chunk -- whose copy nothing overlaps -- is at most one wave
+    std::vector<int64_t> sizes;
+    {
+        int64_t rem = N;
+        const int64_t first = wave < rem ? wave : rem;
+        sizes.push_back(first);
+        rem -= first;
+        while (rem > 2 * wave) { sizes.push_back(2 * wave); rem -= 2 * wave; }
+        if (rem > wave) { sizes.push_back(wave); rem -= wave; }
+        if (rem > 0) sizes.push_back(rem);
+    }
+    const int64_t nchunks = (int64_t)sizes.size();
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_xe0 = al(sizeof(float) * N * 5), b_xref = al(sizeof(float) * 5 * (T + 1)),
                  b_uref = al(sizeof(float) * 2 * (T > 0 ? T : 1));
@@ -189,8 +201,9 @@ int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const
     DP_CUDA(cudaMemcpyAsync(d_xref, xref, sizeof(float) * 5 * (T + 1), cudaMemcpyHostToDevice, st));
     if (T > 0) DP_CUDA(cudaMemcpyAsync(d_uref, uref, sizeof(float) * 2 * T, cudaMemcpyHostToDevice, st));
     DP_CUDA(cudaMemsetAsync(d_st, 0, 2 * sizeof(int), st));
-    for (int64_t k = 0; k < nchunks; ++k) {
-        const int64_t off = k * chunk, n = (off + chunk <= N) ? chunk : N - off;
+    int64_t off = 0;
+    for (int64_t k = 0; k < nchunks; off += sizes[k], ++k) {
+        const int64_t n = sizes[k];
         const int b = (int)(k & 1);
         DP_CUDA(cudaMemcpyAsync(d_xe0 + off * 5, xe0 + off * 5, sizeof(float) * n * 5, cudaMemcpyHostToDevice, st));
         if (rho0) DP_CUDA(cudaMemcpyAsync(d_rho0 + off, rho0 + off, sizeof(float) * n, cudaMemcpyHostToDevice, st));

@@ -91,6 +91,22 @@ def test_rollout_host_buffers_and_strided_store(car, impl):
     assert_states_close(xe_s, g["xe_traj"], g["xref"][:, ::10], "host")
 
 
+def test_rollout_host_chunking_equals_one_device_launch(car, args):
+    """dp_rollout_host processes the samples in chunks (one wave, then two waves each) and copies chunk k to the host while
+    chunk k+1 runs; with more than three chunks (N > 5 waves) and a ragged tail the result must be bit-identical to one device
+    launch over all samples, including the clip margins."""
+    torch.manual_seed(11)
+    T, N = 12, 5 * 2 * 128 * 148 + 4321
+    up, uref, xref = car.get_valid_ref(args)
+    uref, xref = uref[:, :, :T], xref[:, :, :T + 1]
+    xe0 = car.sample_xe0(N)
+    xh, rh, mh = car.compute_density(xe0, xref, uref, args.dt_sim, log_density=True, stride=4, return_margin=True)
+    xd, rd, md = car.compute_density(xe0.cuda(), xref.cuda(), uref.cuda(), args.dt_sim, log_density=True, stride=4,
+                                     return_margin=True)
+    assert not xh.is_cuda and xd.is_cuda
+    assert torch.equal(xh, xd.cpu()) and torch.equal(rh, rd.cpu()) and torch.equal(mh, md.cpu())
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 def test_rollout_modes(car, impl):
     g = golden("rollout_modes.npz")
