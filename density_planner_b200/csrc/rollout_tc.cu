@@ -545,7 +545,9 @@ __device__ __forceinline__ void sample_advance(const RolloutParams &p, SampleSta
 template <int TP, int KC, int BATCH, int TR, int SG>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the warp index through redux.sync: the compiler then knows that everything derived from it (group, feature half,
+    // TMEM lane quarter, hence every tcgen05 address) is warp-uniform and keeps it on the uniform datapath
+    const int tid = threadIdx.x, warp = (int)__reduce_max_sync(0xffffffffu, (unsigned)(tid >> 5)), lane = tid & 31;
     const int grp = warp / GW, wl = warp % GW, q = wl & 3, h = wl >> 2;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
     uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 32);
