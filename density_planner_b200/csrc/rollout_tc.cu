@@ -406,39 +406,56 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     publish(c);  // every read of RA (outputs, parked gates) of this thread has completed
     issue(c, ISSUER_M2, [&] { mma_tangent<TP>(c.RA, c.RD, w2h, w2l, idesc128); });
     TRACE(9);
+    // Row pairs in packed fp32x2: the layer-3 rows of net a are permuted in the operand image (perm_a) so that the
+    // accumulator columns of rows (r, r + 1) for one xe component are neighbours: v[8 k + 2 c + e] <-> w1[6 h + 2 k + e][c].
+    const float2 os2 = make_float2(OSCALE, OSCALE);
     if (NET == 0) {
         const float4 xe = error_state(st, ref);
+        const float2 *b3p = reinterpret_cast<const float2 *>(b3 + 24 * h);
+        const float2 xx = make_float2(xe.x, xe.x), xy = make_float2(xe.y, xe.y), xz = make_float2(xe.z, xe.z), xw = make_float2(xe.w, xe.w);
 #pragma unroll
-        for (int rr = 0; rr < 6; ++rr) {
-            const int r = 6 * h + rr;
-            const float4 bb = *reinterpret_cast<const float4 *>(b3 + 4 * r);
-            const float w0 = fmaf(__uint_as_float(v[4 * rr + 0]), OSCALE, bb.x);
-            const float w1 = fmaf(__uint_as_float(v[4 * rr + 1]), OSCALE, bb.y);
-            const float w2 = fmaf(__uint_as_float(v[4 * rr + 2]), OSCALE, bb.z);
-            const float w3 = fmaf(__uint_as_float(v[4 * rr + 3]), OSCALE, bb.w);
-            float z = w0 * xe.x;
-            z = fmaf(w1, xe.y, z);
-            z = fmaf(w2, xe.z, z);
-            z = fmaf(w3, xe.w, z);
-            const float tz = tanh_fast(z);
-            gz[rr] = fmaf(-tz, tz, 1.0f);
-            c.sZ[(0 * 12 + r) * TILE + c.s] = tz;
-            c.sZ[(1 * 12 + r) * TILE + c.s] = gz[rr] * w2;  // + d xe2 / d theta * w1[r][2]
-            c.sZ[(2 * 12 + r) * TILE + c.s] = gz[rr] * w3;  // + d xe3 / d v * w1[r][3]
+        for (int k = 0; k < 3; ++k) {
+            const int r = 6 * h + 2 * k;
+            const float2 w0 = __ffma2_rn(as_f2(v[8 * k + 0], v[8 * k + 1]), os2, b3p[4 * k + 0]);
+            const float2 w1 = __ffma2_rn(as_f2(v[8 * k + 2], v[8 * k + 3]), os2, b3p[4 * k + 1]);
+            const float2 w2 = __ffma2_rn(as_f2(v[8 * k + 4], v[8 * k + 5]), os2, b3p[4 * k + 2]);
+            const float2 w3 = __ffma2_rn(as_f2(v[8 * k + 6], v[8 * k + 7]), os2, b3p[4 * k + 3]);
+            float2 z = __fmul2_rn(w0, xx);
+            z = __ffma2_rn(w1, xy, z);
+            z = __ffma2_rn(w2, xz, z);
+            z = __ffma2_rn(w3, xw, z);
+            float2 tz, g;
+            tanh_gate2(__fmul2_rn(z, make_float2(TWO_LOG2E, TWO_LOG2E)), tz, g);
+            gz[2 * k] = g.x;
+            gz[2 * k + 1] = g.y;
+            const float2 ga = __fmul2_rn(g, w2), gb = __fmul2_rn(g, w3);  // + d xe2 / d theta * w1[r][2], + d xe3 / d v * w1[r][3]
+            c.sZ[(0 * 12 + r) * TILE + c.s] = tz.x;
+            c.sZ[(0 * 12 + r + 1) * TILE + c.s] = tz.y;
+            c.sZ[(1 * 12 + r) * TILE + c.s] = ga.x;
+            c.sZ[(1 * 12 + r + 1) * TILE + c.s] = ga.y;
+            c.sZ[(2 * 12 + r) * TILE + c.s] = gb.x;
+            c.sZ[(2 * 12 + r + 1) * TILE + c.s] = gb.y;
         }
     } else {
+        // v[2 k + e] <-> w2[0][6 h + 2 k + e], v[8 + 2 k + e] <-> w2[1][6 h + 2 k + e]; even and odd rows are summed apart
+        float2 s0 = make_float2(0.0f, 0.0f), s1 = s0, s2 = s0, s3 = s0;
 #pragma unroll
-        for (int rr = 0; rr < 6; ++rr) {
-            const int r = 6 * h + rr;
-            const float d0 = __uint_as_float(v[rr]);
-            const float d1 = __uint_as_float(v[8 + rr]);
-            const float w20 = fmaf(d0, OSCALE, b3[r]), w21 = fmaf(d1, OSCALE, b3[12 + r]);
-            const float tz = c.sZ[(0 * 12 + r) * TILE + c.s];
-            acc[0] = fmaf(w20, tz, acc[0]);
-            acc[1] = fmaf(w21, tz, acc[1]);
-            acc[2] = fmaf(w20, c.sZ[(1 * 12 + r) * TILE + c.s], acc[2]);
-            acc[3] = fmaf(w21, c.sZ[(2 * 12 + r) * TILE + c.s], acc[3]);
+        for (int k = 0; k < 3; ++k) {
+            const int r = 6 * h + 2 * k;
+            const float2 w20 = __ffma2_rn(as_f2(v[2 * k], v[2 * k + 1]), os2, *reinterpret_cast<const float2 *>(b3 + r));
+            const float2 w21 = __ffma2_rn(as_f2(v[8 + 2 * k], v[8 + 2 * k + 1]), os2, *reinterpret_cast<const float2 *>(b3 + 12 + r));
+            const float2 tz = make_float2(c.sZ[(0 * 12 + r) * TILE + c.s], c.sZ[(0 * 12 + r + 1) * TILE + c.s]);
+            const float2 za = make_float2(c.sZ[(1 * 12 + r) * TILE + c.s], c.sZ[(1 * 12 + r + 1) * TILE + c.s]);
+            const float2 zb = make_float2(c.sZ[(2 * 12 + r) * TILE + c.s], c.sZ[(2 * 12 + r + 1) * TILE + c.s]);
+            s0 = __ffma2_rn(w20, tz, s0);
+            s1 = __ffma2_rn(w21, tz, s1);
+            s2 = __ffma2_rn(w20, za, s2);
+            s3 = __ffma2_rn(w21, zb, s3);
         }
+        acc[0] += s0.x + s0.y;
+        acc[1] += s1.x + s1.y;
+        acc[2] += s2.x + s2.y;
+        acc[3] += s3.x + s3.y;
     }
     await(c, ph);
     TRACE(10);
@@ -474,9 +491,11 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         TRACE(12 + 2 * k);
     }
 
-    // ---- R56: layer-3 tangent outputs ---------------------------------------------------------------------------------------------
+    // ---- R56: layer-3 tangent outputs (same column order as R4) -----------------------------------------------------------------
+    const float2 ts2 = make_float2(TSCALE, TSCALE);
     if (NET == 0) {
         const float4 xe = error_state(st, ref);
+        const float2 xx = make_float2(xe.x, xe.x), xy = make_float2(xe.y, xe.y), xz = make_float2(xe.z, xe.z), xw = make_float2(xe.w, xe.w);
         uint32_t a[24], b[24];
         ld8(c.ra + 24 * h, a);
         ld8(c.ra + 24 * h + 8, a + 8);
@@ -486,19 +505,23 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         ld8(c.ra + N3 + 24 * h + 16, b + 16);
         wait_ld();
 #pragma unroll
-        for (int rr = 0; rr < 6; ++rr) {
-            const int r = 6 * h + rr;
-            float dzt = __uint_as_float(a[4 * rr + 0]) * xe.x;
-            dzt = fmaf(__uint_as_float(a[4 * rr + 1]), xe.y, dzt);
-            dzt = fmaf(__uint_as_float(a[4 * rr + 2]), xe.z, dzt);
-            dzt = fmaf(__uint_as_float(a[4 * rr + 3]), xe.w, dzt);
-            float dzv = __uint_as_float(b[4 * rr + 0]) * xe.x;
-            dzv = fmaf(__uint_as_float(b[4 * rr + 1]), xe.y, dzv);
-            dzv = fmaf(__uint_as_float(b[4 * rr + 2]), xe.z, dzv);
-            dzv = fmaf(__uint_as_float(b[4 * rr + 3]), xe.w, dzv);
-            const float gi = gz[rr] * TSCALE;
-            c.sZ[(1 * 12 + r) * TILE + c.s] = fmaf(gi, dzt, c.sZ[(1 * 12 + r) * TILE + c.s]);
-            c.sZ[(2 * 12 + r) * TILE + c.s] = fmaf(gi, dzv, c.sZ[(2 * 12 + r) * TILE + c.s]);
+        for (int k = 0; k < 3; ++k) {
+            const int r = 6 * h + 2 * k;
+            float2 dzt = __fmul2_rn(as_f2(a[8 * k + 0], a[8 * k + 1]), xx);
+            dzt = __ffma2_rn(as_f2(a[8 * k + 2], a[8 * k + 3]), xy, dzt);
+            dzt = __ffma2_rn(as_f2(a[8 * k + 4], a[8 * k + 5]), xz, dzt);
+            dzt = __ffma2_rn(as_f2(a[8 * k + 6], a[8 * k + 7]), xw, dzt);
+            float2 dzv = __fmul2_rn(as_f2(b[8 * k + 0], b[8 * k + 1]), xx);
+            dzv = __ffma2_rn(as_f2(b[8 * k + 2], b[8 * k + 3]), xy, dzv);
+            dzv = __ffma2_rn(as_f2(b[8 * k + 4], b[8 * k + 5]), xz, dzv);
+            dzv = __ffma2_rn(as_f2(b[8 * k + 6], b[8 * k + 7]), xw, dzv);
+            const float2 gi = __fmul2_rn(make_float2(gz[2 * k], gz[2 * k + 1]), ts2);
+            const float2 za = __ffma2_rn(gi, dzt, make_float2(c.sZ[(1 * 12 + r) * TILE + c.s], c.sZ[(1 * 12 + r + 1) * TILE + c.s]));
+            const float2 zb = __ffma2_rn(gi, dzv, make_float2(c.sZ[(2 * 12 + r) * TILE + c.s], c.sZ[(2 * 12 + r + 1) * TILE + c.s]));
+            c.sZ[(1 * 12 + r) * TILE + c.s] = za.x;
+            c.sZ[(1 * 12 + r + 1) * TILE + c.s] = za.y;
+            c.sZ[(2 * 12 + r) * TILE + c.s] = zb.x;
+            c.sZ[(2 * 12 + r + 1) * TILE + c.s] = zb.y;
         }
     } else {
         // d w2[0][r] / d theta = theta accumulator column r; d w2[1][r] / d v = v accumulator column 12 + r
@@ -506,15 +529,16 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         ld8(c.ra + 6 * h, a);
         ld8(c.ra + N3 + 12 + 6 * h, b);
         wait_ld();
+        float2 s2 = make_float2(0.0f, 0.0f), s3 = s2;
 #pragma unroll
-        for (int rr = 0; rr < 6; ++rr) {
-            const int r = 6 * h + rr;
-            const float dt0 = __uint_as_float(a[rr]) * TSCALE;
-            const float dv1 = __uint_as_float(b[rr]) * TSCALE;
-            const float tz = c.sZ[(0 * 12 + r) * TILE + c.s];
-            acc[2] = fmaf(dt0, tz, acc[2]);
-            acc[3] = fmaf(dv1, tz, acc[3]);
+        for (int k = 0; k < 3; ++k) {
+            const int r = 6 * h + 2 * k;
+            const float2 tz = make_float2(c.sZ[(0 * 12 + r) * TILE + c.s], c.sZ[(0 * 12 + r + 1) * TILE + c.s]);
+            s2 = __ffma2_rn(__fmul2_rn(as_f2(a[2 * k], a[2 * k + 1]), ts2), tz, s2);
+            s3 = __ffma2_rn(__fmul2_rn(as_f2(b[2 * k], b[2 * k + 1]), ts2), tz, s3);
         }
+        acc[2] += s2.x + s2.y;
+        acc[3] += s3.x + s3.y;
     }
     TRACE(15);
     if (TR) ++c.tchain;
@@ -791,13 +815,22 @@ int dp_tc_prepare(dp_controller *c, const float *blob) {
         p += 128 * 128;
         for (int j = 0; j < 128; ++j) sp[SP_B2P + j] = (float)(k * p[j]);
         p += 128;
-        build_split_image(p, nouts[m], nrows3[m], WSCALE, reinterpret_cast<__half *>(img.data() + off_w3h[m]),
+        // layer 3: net a's 48 rows (w1[r][c], output o = 4 r + c) go into the image in the order perm_a(o), which puts the
+        // rows (r, r + 1) of one component c next to each other inside each thread's 24 columns (packed fp32x2 in R4 / R56)
+        std::vector<float> W3(nouts[m] * 128), B3(nouts[m]);
+        for (int o = 0; o < nouts[m]; ++o) {
+            const int r = o / 4, cc = o % 4;
+            const int n = m == 0 ? 24 * (r / 6) + 8 * ((r % 6) / 2) + 2 * cc + (r % 2) : o;
+            memcpy(W3.data() + (size_t)n * 128, p + (size_t)o * 128, sizeof(float) * 128);
+            B3[n] = p[nouts[m] * 128 + o];
+        }
+        build_split_image(W3.data(), nouts[m], nrows3[m], WSCALE, reinterpret_cast<__half *>(img.data() + off_w3h[m]),
                           reinterpret_cast<__half *>(img.data() + off_w3l[m]));
-        for (int r = 0; r < nouts[m]; ++r)
-            sp[SP_B3R + r] = (float)((double)p[nouts[m] * 128 + r] - split_image_rowsum(p, r, WSCALE) / (double)WSCALE);
-        p += nouts[m] * 128;
-        memcpy(sp + SP_B3, p, sizeof(float) * nouts[m]);
-        p += nouts[m];
+        for (int n = 0; n < nouts[m]; ++n) {
+            sp[SP_B3 + n] = B3[n];
+            sp[SP_B3R + n] = (float)((double)B3[n] - split_image_rowsum(W3.data(), n, WSCALE) / (double)WSCALE);
+        }
+        p += nouts[m] * 128 + nouts[m];
     }
     void *d = nullptr;
     DP_CUDA(cudaMalloc(&d, IMAGE_BYTES));
