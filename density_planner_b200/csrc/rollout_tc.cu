@@ -88,10 +88,12 @@ constexpr int OFF_BAR = OFF_REF + NGROUPS * 3 * 8 * 4;          // 2 mbarriers +
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-#ifndef DP_SPLIT_TRUNC
-#define DP_SPLIT_TRUNC 1
+#ifndef DP_SPLIT
+#define DP_SPLIT 2   // 0: F2FP + two conversions back, 1: mantissa truncation (LOP3), 2: mixed-precision FHADD (default)
 #endif
-#if DP_SPLIT_TRUNC
+#if DP_SPLIT == 2
+#define SPLIT split_h2_mixed
+#elif DP_SPLIT == 1
 #define SPLIT split_h2_trunc
 #else
 #define SPLIT split_h2
