@@ -39,7 +39,11 @@
 //   * the epilogue math is packed fp32x2 (FFMA2 / FADD2 / FMUL2) with pre-scaled biases: pre-activations arrive already
 //     multiplied by 2 log2(e); tanh|x| = 2 / (1 + 2^-|y|) - 1 with the sign copied from y, four reciprocals share one
 //     MUFU.RCP (tc_ptx.cuh).  The part of the layer-1 pre-activation that is the same for every sample of a time index
-//     is computed once per step per group.
+//     is computed once per step per group.  When the weights bound the layer-2 pre-activations (SG kernels, chosen by
+//     the host) layer 2 needs no |y| / sign copy and hands r = (1 + h2) / 2 to layer 3.  The fp16 hi/lo split uses the
+//     mixed-precision add (FHADD): hi = RN(v) for a pair in one F2FP, lo = v - hi one instruction per element.
+//   * the warp index goes through redux.sync once, so that the compiler knows group / half / lane quarter -- and every
+//     tcgen05 address built from them -- to be warp-uniform (uniform registers, uniform branches, no R2UR per access).
 //   * both threads of a sample (feature halves h = 0, 1) carry the sample state redundantly in registers, so the Euler
 //     step needs one exchange of four partial head sums through shared memory and no broadcast of the next input.
 //   * 224 KB of shared memory leave the L1 no room: every global load and every register spill reload is an L2 round
@@ -178,7 +182,7 @@ __device__ __forceinline__ void mma_tangent_k(uint32_t d, uint32_t a0, uint64_t 
 
 // K-chunked issue: in iteration i of an operand-producing loop every thread has just stored its 16-feature chunk
 // (chunks i and 4 + i of the tile are complete once the whole group got here).  The other warps only ARRIVE on the
-// chunk's named barrier and carry on with the next chunk; the leader warp waits for them and issues the MMAs of those
+// chunk's named barrier and carry on with the next chunk; the issuing warp waits for them and issues the MMAs of those
 // two K-chunks, so the tensor pipe works through the batch while the CUDA cores are still producing the rest of it.
 template <typename F>
 __device__ __forceinline__ void chunk_issue(const Ctx &c, int who, int i, bool last, F &&f) {
