@@ -42,6 +42,7 @@ _SIGNATURES = {
     "dp_rollout": (_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _int, _uint, _int, _vp, _vp, _i64, _vp, _vp, _vp]),
     "dp_rollout_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i64, _int, _uint, _int, _vp, _vp, _i64, _vp, _vp, _vp]),
     "dp_rollout_host": (_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _int, _uint, _int, _vp, _vp, _vp, _vp]),
+    "dp_host_chunk_schedule": (_int, [_i64, _i64, _vp, _int]),
     "dp_step": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dp_pos2gridpos": (_int, [ctypes.POINTER(GridGeom), _vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),
     "dp_gridpos2pos": (_int, [ctypes.POINTER(GridGeom), _vp, _vp, _i64, _vp, _vp, _vp]),

@@ -141,6 +141,24 @@ static int ws_reserve(dp_controller *c, size_t bytes) {
     return 0;
 }
 
+// Chunk sizes of dp_rollout_host (pure host logic, no CUDA call): one wave first (the copy engine starts early), then two
+// waves per chunk, and what is left split so that the last chunk -- the only copy nothing overlaps -- is at most one wave.
+int dp_host_chunk_schedule(int64_t N, int64_t wave, int64_t *sizes, int max_chunks) {
+    if (N <= 0 || wave <= 0 || !sizes) return 0;
+    int n = 0;
+    int64_t rem = N;
+    auto push = [&](int64_t v) {
+        if (n < max_chunks) sizes[n] = v;
+        ++n;
+        rem -= v;
+    };
+    push(wave < rem ? wave : rem);
+    while (rem > 2 * wave) push(2 * wave);
+    if (rem > wave) push(wave);
+    if (rem > 0) push(rem);
+    return n <= max_chunks ? n : -n;
+}
+
 int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const float *uref, const float *rho0, float dt,
                     int64_t N, int T, unsigned flags, int stride, float *x_out, float *rho_out, float *clip_margin,
                     int *status) {
@@ -158,17 +176,9 @@ int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const
     if (chunk > N) chunk = N;
     // the first chunk is a single wave, so that the copy engine starts after one wave instead of two, and what is left at
     // the end is split so that the last chunk -- whose copy nothing overlaps -- is at most one wave
-    std::vector<int64_t> sizes;
-    {
-        int64_t rem = N;
-        const int64_t first = wave < rem ? wave : rem;
-        sizes.push_back(first);
-        rem -= first;
-        while (rem > 2 * wave) { sizes.push_back(2 * wave); rem -= 2 * wave; }
-        if (rem > wave) { sizes.push_back(wave); rem -= wave; }
-        if (rem > 0) sizes.push_back(rem);
-    }
-    const int64_t nchunks = (int64_t)sizes.size();
+    std::vector<int64_t> sizes((size_t)(N / (2 * wave) + 4));
+    const int64_t nchunks = dp_host_chunk_schedule(N, wave, sizes.data(), (int)sizes.size());
+    DP_REQUIRE(nchunks > 0, "dp_rollout_host: chunk schedule");
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_xe0 = al(sizeof(float) * N * 5), b_xref = al(sizeof(float) * 5 * (T + 1)),
                  b_uref = al(sizeof(float) * 2 * (T > 0 ? T : 1));

@@ -93,10 +93,15 @@ int dp_rollout_batch(const dp_controller *c, const float *xe0, const float *xref
                      const float *rho0, float dt, int64_t R, int64_t n_per_ref, int T, unsigned flags, int stride,
                      float *x_out, float *rho_out, int64_t ldn, float *clip_margin, int *status, void *stream);
 
-/* Same with HOST buffers (x_out/rho_out host, ld = N); status is a host int[2].  Copies are part of the call. */
+/* Same with HOST buffers (x_out/rho_out host, ld = N); status is a host int[2].  Copies are part of the call: the samples
+ * are processed in chunks and the device->host copy of chunk k overlaps the rollout of chunk k+1. */
 int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const float *uref, const float *rho0,
                     float dt, int64_t N, int T, unsigned flags, int stride, float *x_out, float *rho_out,
                     float *clip_margin, int *status);
+
+/* Chunk sizes dp_rollout_host uses for N samples when one wave (two 128-sample tiles per SM) holds `wave` samples: writes
+ * up to max_chunks sizes, returns their number (negative: max_chunks too small), 0 for N <= 0.  Host logic only, no device. */
+int dp_host_chunk_schedule(int64_t N, int64_t wave, int64_t *sizes, int max_chunks);
 
 /*
  * Single-step API: u_func (:26), f_func (:43), dudx_func (:69), dfdx_func (:93), divf_func (:116) of

@@ -29,6 +29,23 @@ def test_library_exports_every_declared_symbol(dp):
     assert dp.lib().dp_abi_version() == 1
 
 
+def test_host_chunk_schedule(dp):
+    """dp_rollout_host's chunk schedule (host logic, no device): sizes add up to N, no chunk exceeds two waves (the size of
+    the device staging buffers), the first chunk is at most one wave (the copy engine starts early) and so is the last one
+    (its copy is the only one nothing overlaps)."""
+    L = dp.lib()
+    wave = 2 * 128 * 148
+    buf = (ctypes.c_int64 * 64)()
+    for N in [1, 19, wave - 1, wave, wave + 1, 2 * wave, 3 * wave, 3 * wave + 1, 4 * wave + 5, 1_000_000, 26 * wave, 27 * wave - 3]:
+        n = L.dp_host_chunk_schedule(N, wave, buf, 64)
+        sizes = list(buf[:n])
+        assert n >= 1 and sum(sizes) == N and all(0 < s <= 2 * wave for s in sizes), (N, sizes)
+        assert sizes[0] <= wave and sizes[-1] <= wave, (N, sizes)
+        assert n <= N // (2 * wave) + 3
+    assert L.dp_host_chunk_schedule(0, wave, buf, 64) == 0
+    assert L.dp_host_chunk_schedule(10 * wave, wave, buf, 2) < 0  # too small a buffer is reported, not overrun
+
+
 def test_library_is_sm100a_native():
     """The shipped .so carries sm_100a SASS (no PTX-JIT path, no other arch)."""
     import subprocess
