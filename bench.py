@@ -4,15 +4,21 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework's arm
     python bench.py --impl reference [--gpus N] ...                 # CPU arm: the oracle port on the host cores
 
-One "step" = one pass of the hot path over one batch of synthetic input on every rank:
+One "step" = one pass of the hot path over one batch of synthetic input on every rank, through the device-resident
+pipeline (density_planner_b200/pipeline.py, dp_pipeline_*):
     fused rollout of SAMPLES x STEPS closed-loop sample-steps with Liouville log-density (BASELINE config 2:
-    1M samples x 100 steps), slices stored every 10th step  ->  density normaliser  ->  collision cost on the stored
-    slices  ->  occupancy binning of the slices (int64/int32 grids) fused with the obstacle-grid dot product
-    [-> NCCL allreduce of normaliser stats, cost, dot product and grids when N > 1].
+    1M samples x 100 steps); the (x, y) slices and the log-density of every 10th step stay on the device, the per-slice
+    max of the log-density is reduced inside the rollout  [-> NCCL allreduce MAX of Ts floats when N > 1]
+    ->  ONE pass over the stored slices: density weights, int64/int32 occupancy grids and the collision cost in int64 fixed
+    point  [-> ONE NCCL allreduce SUM of that integer buffer when N > 1]  ->  per-slice normalisation.
 `value` = closed-loop sample-steps/s over all ranks with inputs resident in HBM (CUDA events, max over ranks).
-`e2e`   = the same metric through the public API `Car.compute_density` with HOST tensors (H2D + kernel + D2H of the
-          full trajectory inside the timed region).
-Multi-GPU is weak scaling: every rank rolls out its own SAMPLES samples; no collective in the rollout.
+`e2e`   = the same metric through the public API `OccupancyPipeline.run` with HOST tensors: pinned xe0 / rho0 in (H2D),
+          grids + per-slice costs out (D2H), both inside the timed region.  `e2e_trajectory` is the other public route,
+          `Car.compute_density` with host tensors, which returns the full (N,5,T+1)+(N,1,T+1) trajectory (2.4 GB per step).
+`config5` = BASELINE config 5: 100M samples x 100 steps in total (100M / N per rank), host samples in, allreduced grids +
+          cost out; the integer results are bit-identical at 1/2/4/8 GPUs (`checks`).
+Multi-GPU is weak scaling for `value` / `e2e` (every rank rolls out its own SAMPLES samples), strong for `config5`; there is
+no collective in the rollout.
 """
 import argparse
 import json
@@ -29,6 +35,11 @@ SAMPLES = 1_000_000
 STEPS = 100
 STRIDE = 10
 FLOP_PER_SAMPLE_STEP = 248_288  # SURVEY section 8d / DESIGN.md: algorithmic FLOPs (124,144 MAC) per sample-step
+# executed tensor-pipe work: value rows (43,008 MAC) run 3 split-fp16 products, tangent rows (80,896 MAC) one; the head sums
+# (240 MAC) run on CUDA cores
+EXECUTED_MMA_FLOP_PER_SAMPLE_STEP = 2 * (3 * 43_008 + 80_896)
+CONFIG5_SAMPLES = 100_000_000
+BLOCK = 1_000_000  # config 5 samples are generated in seeded blocks of 1M so that the global set is the same at every N
 METRIC = "closed-loop sample-steps/sec with Liouville density"
 UNIT = "sample-steps/s"
 
@@ -186,15 +197,49 @@ def run_reference_arm(opts):
     print(json.dumps(line))
 
 
+def config5_samples(car, rank, world, total):
+    """The rank's shard of the GLOBAL config-5 sample set: blocks of BLOCK samples, block b drawn with seed 5000 + b, so the
+    union over ranks is the same set at every world size (which is what makes the integer results comparable across N)."""
+    import torch
+    nblocks = (total + BLOCK - 1) // BLOCK
+    from density_planner_b200.dist import shard_range
+    b_lo, b_hi = shard_range(nblocks, rank, world)
+    n = sum(min(BLOCK, total - b * BLOCK) for b in range(b_lo, b_hi))
+    xe0 = torch.empty((n, 5, 1), dtype=torch.float32, pin_memory=True)
+    rho0 = torch.empty((n,), dtype=torch.float32, pin_memory=True)
+    off = 0
+    for b in range(b_lo, b_hi):
+        k = min(BLOCK, total - b * BLOCK)
+        torch.manual_seed(5000 + b)
+        xe0[off:off + k] = car.sample_xe0(k)
+        rho0[off:off + k] = torch.rand(k) + 0.5
+        off += k
+    return xe0, rho0
+
+
+def grid_checks(res):
+    """Integer fingerprints of a pipeline result (identical for any sharding of the same global sample set)."""
+    import torch
+    m = res.mass.reshape(res.mass.shape[0], -1)
+    c = res.count.reshape(res.count.shape[0], -1).to(torch.int64)
+    pos = (torch.arange(m.shape[1], device=m.device, dtype=torch.int64) % 1009) + 1
+    return {"grid_mass_total": int(m.sum().item()), "grid_count_total": int(c.sum().item()),
+            "grid_mass_checksum": int(((m % 1000003) * pos).sum().item()),
+            "grid_count_checksum": int((c * pos).sum().item()),
+            "cost_fixed_total": int(res.cost_fixed.sum().item()),
+            "cost_total": float(res.cost_slices.sum().item()), "occupancy_dot_total": float(res.occ_dot.sum().item())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--kernel", default=None, choices=[None, "ffma", "tc"], help="rollout kernel (default: library default)")
     ap.add_argument("--samples", type=int, default=SAMPLES)
+    ap.add_argument("--config5-samples", type=int, default=CONFIG5_SAMPLES, help="total samples of the config-5 block (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-trajectory-e2e", action="store_true")
     opts = ap.parse_args()
     if opts.impl == "reference":
         return run_reference_arm(opts)
@@ -207,6 +252,7 @@ def main():
     import torch
     import density_planner_b200 as dp
     from density_planner_b200 import _lib, dist as D, grid as G
+    from density_planner_b200.pipeline import OccupancyPipeline
     import ctypes
 
     rank, world, local_rank = D.init_from_env()
@@ -220,69 +266,53 @@ def main():
     car = dp.Car(args, device=dev)
     N, T, Ts = opts.samples, STEPS, STEPS // STRIDE + 1
 
-    # ---- synthetic inputs (seeded; rank r uses seed r for its samples) --------------------------------------------
+    # ---- synthetic inputs (seeded; rank r uses seed 1000 + r for its samples) ---------------------------------------
     torch.manual_seed(0)
     up, uref, xref = car.get_valid_ref(args)
     uref, xref = uref[:, :, :T].contiguous(), xref[:, :, :T + 1].contiguous()
     torch.manual_seed(1000 + rank)
     xe0_host = car.sample_xe0(N).pin_memory()
-    rho0_host = (torch.rand(N) + 0.5)
-    rho0_host = (rho0_host / (rho0_host.sum() * world)).pin_memory()
-    xe0 = xe0_host.reshape(N, 5).to(dev)
+    rho0_host = (torch.rand(N) + 0.5).pin_memory()   # unnormalised sample weights in [0.5, 1.5): independent of N and world
+    xe0 = xe0_host.to(dev)
     rho0 = rho0_host.to(dev)
-    xref_d, uref_d = xref.reshape(5, T + 1).to(dev), uref.reshape(2, T).to(dev)
+    xref_d, uref_d = xref.to(dev), uref.to(dev)
     grid, gx, gy = synthetic_env(args, 0, dev)
     denv = dp.DeviceEnv(grid, gx, gy, args, device=dev)
     del grid, gx, gy
-
-    impl_flag = {None: _lib.DP_IMPL_DEFAULT, "ffma": _lib.DP_IMPL_FFMA, "tc": _lib.DP_IMPL_TC}[opts.kernel]
-    flags = _lib.DP_LOG_DENSITY | _lib.DP_DENSITY | impl_flag
-    x_out = torch.empty((Ts, 5, N), dtype=torch.float32, device=dev)
-    l_out = torch.empty((Ts, N), dtype=torch.float32, device=dev)
-    rho = torch.empty((Ts, N), dtype=torch.float32, device=dev)
-    lmax = torch.empty(Ts, dtype=torch.float32, device=dev)
-    lsum = torch.empty(Ts, dtype=torch.float64, device=dev)
-    cost_slices = torch.empty(Ts, dtype=torch.float64, device=dev)
-    occ_dot = torch.empty(Ts, dtype=torch.float64, device=dev)
-    spec = _lib.BinSpec()
-    spec.mode = 0
-    spec.geom = G._geom(args)
-    spec.mass_scale_log2 = G.mass_scale_log2(N * world, 1.0)
-    cells = (args.grid_size[0] + 1) * (args.grid_size[1] + 1)
-    mass = torch.zeros((Ts, cells), dtype=torch.int64, device=dev)
-    count = torch.zeros((Ts, cells), dtype=torch.int32, device=dev)
+    cap5 = 0
+    if opts.config5_samples > 0:
+        nb = (opts.config5_samples + BLOCK - 1) // BLOCK
+        b_lo, b_hi = D.shard_range(nb, rank, world)
+        cap5 = (b_hi - b_lo) * BLOCK
+    pipe = OccupancyPipeline(car, denv, args, T, STRIDE, max(N, cap5, 1), rho0_bound=2.0)
     stream = torch.cuda.current_stream(dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
     ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(opts.steps)]
     ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(opts.steps)]
     launches = {"n": 0}
+    lmax = torch.empty(Ts, dtype=torch.float32, device=dev)
+    ibuf = torch.empty(pipe.words, dtype=torch.int64, device=dev)
+    out3 = torch.empty((3, Ts), dtype=torch.float64, device=dev)
+    xe0_f, xref_f, uref_f = xe0.reshape(N, 5), xref_d.reshape(5, T + 1), uref_d.reshape(2, T)
 
     def one_step(i_timed=None):
+        # the body of OccupancyPipeline.run for device inputs, with events around phase 1 (the rollout kernel; the four
+        # device-to-device input copies and two tiny kernels inside that call are < 0.1 % of it)
         if i_timed is not None:
             ev_k0[i_timed].record(stream)
-        _lib.check(L.dp_rollout(car.controller.controller.handle, _lib.ptr(xe0), _lib.ptr(xref_d), _lib.ptr(uref_d), None,
-                                float(args.dt_sim), N, T, flags, STRIDE, _lib.ptr(x_out), _lib.ptr(l_out), N, None, None,
-                                sp), "dp_rollout")
+        _lib.check(L.dp_pipeline_rollout(pipe.handle, _lib.ptr(xe0_f), _lib.ptr(rho0), _lib.ptr(xref_f), _lib.ptr(uref_f), 0,
+                                         float(args.dt_sim), N, _lib.ptr(lmax), sp), "dp_pipeline_rollout")
         if i_timed is not None:
             ev_k1[i_timed].record(stream)
-        _lib.check(L.dp_normalize_stats(_lib.ptr(l_out), _lib.ptr(rho0), N, Ts, N, _lib.ptr(lmax), _lib.ptr(lsum), sp),
-                   "dp_normalize_stats")
-        gmax, gsum = D.merge_normalizer_stats(lmax, lsum)
-        _lib.check(L.dp_normalize_apply(_lib.ptr(l_out), _lib.ptr(rho0), N, Ts, N, _lib.ptr(gmax), _lib.ptr(gsum),
-                                        _lib.ptr(rho), sp), "dp_normalize_apply")
-        xs, ys = x_out[:, 0, :], x_out[:, 1, :]
-        _lib.check(L.dp_cost_coll(denv.handle, _lib.ptr(xs), _lib.ptr(ys), 1, 5 * N, _lib.ptr(rho), 1, N, N, Ts, 0,
-                                  _lib.ptr(cost_slices), None, None, None, None, 0, 0, None, sp), "dp_cost_coll")
-        mass.zero_()
-        count.zero_()
-        _lib.check(L.dp_bin2d_occ(ctypes.byref(spec), denv.handle, _lib.ptr(xs), _lib.ptr(ys), 1, 5 * N, _lib.ptr(rho), 1, N,
-                                  N, Ts, _lib.ptr(mass), _lib.ptr(count), _lib.ptr(occ_dot), sp), "dp_bin2d_occ")
-        D.allreduce_sum(cost_slices)
-        D.allreduce_sum(occ_dot)
-        D.allreduce_grids(mass, count)
-        # rollout, normaliser (max, sum, finalize, apply), cost (+finalize), 2 memsets, binning fused with the occupancy dot
-        # product (+finalize)  (+ NCCL kernels when N > 1)
-        launches["n"] += 11
+        if world > 1:
+            torch.distributed.all_reduce(lmax, op=torch.distributed.ReduceOp.MAX)
+        _lib.check(L.dp_pipeline_bin(pipe.handle, _lib.ptr(lmax), _lib.ptr(ibuf), sp), "dp_pipeline_bin")
+        if world > 1:
+            torch.distributed.all_reduce(ibuf, op=torch.distributed.ReduceOp.SUM)
+        _lib.check(L.dp_pipeline_finalize(pipe.handle, _lib.ptr(ibuf), _lib.ptr(out3), sp), "dp_pipeline_finalize")
+        # kernels of this library per step: rollout, lmax decode, fused binning + cost, finalize (+ 2 memsets, 4 D2D copies,
+        # + the NCCL kernels when N > 1)
+        launches["n"] += 4
 
     def barrier():
         if world > 1:
@@ -309,65 +339,91 @@ def main():
     value = world * N * T / (ms_step * 1e-3)
     k_ms = sum(a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)) / opts.steps
     k_ms = D.max_over_ranks(k_ms, dev)
-    total_mass = int(mass.sum().item())
-    total_count = int(count.sum().item())
-    cost_total = float(cost_slices.sum().item())
+    from density_planner_b200.pipeline import OccupancyResult
+    checks = grid_checks(OccupancyResult(ibuf, out3, Ts, pipe.cx, pipe.cy, pipe.spec.mass_scale_log2, pipe.cost_scale_log2))
+    checks["samples_total"] = world * N
 
-    # ---- end to end through the public API with host tensors ---------------------------------------------------------
-    Ne = min(N, SAMPLES)  # the full (N,5,T+1)+(N,1,T+1) trajectory comes back to the host: cap it at the config-2 size
-    xe0_cpu = xe0_host[:Ne]  # (Ne,5,1) pinned
-    impl = opts.kernel
-    # warm the host path at full size (pinned result buffers come from torch's caching host allocator afterwards)
-    _w = car.compute_density(xe0_cpu, xref, uref, args.dt_sim, log_density=True, cutting=True, impl=impl)
-    del _w
+    # ---- end to end through the public API with host tensors: pinned samples in, grids + costs out ------------------------
+    res = pipe.run(xe0_host, rho0_host, xref, uref, args.dt_sim, to_host=True)  # warm the host path (pinned result buffers)
     barrier()
-    e2e_steps = max(1, min(opts.steps, 3))
-    t_sum = 0.0
-    xe_traj = rho_traj = None
-    for _ in range(e2e_steps):
-        xe_traj = rho_traj = None  # the caller has consumed and dropped the previous result
-        t0 = time.perf_counter()
-        xe_traj, rho_traj = car.compute_density(xe0_cpu, xref, uref, args.dt_sim, log_density=True, cutting=True, impl=impl)
-        _ = float(rho_traj[0, 0, -1])
-        t_sum += time.perf_counter() - t0
-    t_e2e = D.max_over_ranks(t_sum / e2e_steps, dev)
-    # context for the e2e number: the raw pinned device->host copy rate of this box for the same byte count
-    probe_dev = torch.empty((T + 1) * 6 * Ne, dtype=torch.float32, device=dev)
-    probe_host = torch.empty((T + 1) * 6 * Ne, dtype=torch.float32, pin_memory=True)
-    probe_host.copy_(probe_dev)
-    torch.cuda.synchronize(dev)
+    e2e_steps = max(1, opts.steps)
     t0 = time.perf_counter()
-    probe_host.copy_(probe_dev)
-    torch.cuda.synchronize(dev)
-    d2h_gbs = probe_dev.numel() * 4 / (time.perf_counter() - t0) / 1e9
-    del probe_dev, probe_host
-    e2e = {"value": world * Ne * T / t_e2e, "unit": UNIT, "samples_per_gpu": Ne,
-           "h2d_bytes_per_step": int(4 * (Ne * 5 + 5 * (T + 1) + 2 * T)),
-           "d2h_bytes_per_step": int(4 * (T + 1) * 6 * Ne),
-           "api": "Car.compute_density(xe0, xref_traj, uref_traj, dt, log_density=True) with CPU tensors "
-                  "(dp_rollout_host: H2D + kernel + D2H of the full (N,5,T+1)+(N,1,T+1) trajectory)",
-           "ms_per_step": 1e3 * t_e2e, "pinned_d2h_gbs_measured": d2h_gbs, "numa_node_rank0": numa_node}
-    del xe_traj, rho_traj
+    for _ in range(e2e_steps):
+        res = pipe.run(xe0_host, rho0_host, xref, uref, args.dt_sim, to_host=True)
+        _ = float(res.cost_slices[-1]) + float(res.mass[0, 0, 0])  # the caller reads the result
+    t_e2e = D.max_over_ranks((time.perf_counter() - t0) / e2e_steps, dev)
+    e2e = {"value": world * N * T / t_e2e, "unit": UNIT, "samples_per_gpu": N,
+           "h2d_bytes_per_step": int(4 * (N * 5 + N + 5 * (T + 1) + 2 * T)),
+           "d2h_bytes_per_step": int(8 * pipe.words + 8 * 3 * Ts),
+           "api": "OccupancyPipeline.run(xe0, rho0, xref_traj, uref_traj, dt, to_host=True) with pinned CPU tensors "
+                  "(dp_rollout_fused at N=1; dp_pipeline_rollout / _bin / _finalize around two allreduces at N>1): H2D of the "
+                  "samples, rollout, fused binning + cost, D2H of the int64 grids / int32 counts / per-slice costs",
+           "ms_per_step": 1e3 * t_e2e, "numa_node_rank0": numa_node}
 
-    # ---- collision cost / binning throughput on the stored slices (second half of the metric) ---------------------
-    xs, ys = x_out[:, 0, :], x_out[:, 1, :]
+    # ---- the other public route: Car.compute_density with host tensors (full trajectory back to the host) -----------------
+    e2e_traj = None
+    if not opts.no_trajectory_e2e:
+        Ne = min(N, SAMPLES)
+        xe0_cpu = xe0_host[:Ne]
+        _w = car.compute_density(xe0_cpu, xref, uref, args.dt_sim, log_density=True, cutting=True)
+        del _w
+        barrier()
+        reps = 2
+        t_sum = 0.0
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            xe_traj, rho_traj = car.compute_density(xe0_cpu, xref, uref, args.dt_sim, log_density=True, cutting=True)
+            _ = float(rho_traj[0, 0, -1])
+            t_sum += time.perf_counter() - t0
+            del xe_traj, rho_traj
+        t_tr = D.max_over_ranks(t_sum / reps, dev)
+        e2e_traj = {"value": world * Ne * T / t_tr, "unit": UNIT, "samples_per_gpu": Ne, "ms_per_step": 1e3 * t_tr,
+                    "h2d_bytes_per_step": int(4 * (Ne * 5 + 5 * (T + 1) + 2 * T)), "d2h_bytes_per_step": int(4 * (T + 1) * 6 * Ne),
+                    "api": "Car.compute_density(xe0, xref_traj, uref_traj, dt, log_density=True) with CPU tensors "
+                           "(dp_rollout_host: H2D + kernel + D2H of the full (N,5,T+1)+(N,1,T+1) trajectory; copy bound)"}
+
+    # ---- BASELINE config 5: 100M samples x 100 steps in total, host samples in, allreduced grids + cost out -----------------
+    cfg5 = None
+    if opts.config5_samples > 0:
+        x5, r5 = config5_samples(car, rank, world, opts.config5_samples)
+        barrier()
+        t0 = time.perf_counter()
+        res5 = pipe.run(x5, r5, xref, uref, args.dt_sim, to_host=True)
+        _ = float(res5.cost_slices[-1])
+        t5 = D.max_over_ranks(time.perf_counter() - t0, dev)
+        cfg5 = {"workload": "BASELINE config 5: %d samples x %d steps in total, %d samples on rank 0; pinned host samples in, "
+                            "allreduced int64 grids + fixed-point cost out" % (opts.config5_samples, T, x5.shape[0]),
+                "value": opts.config5_samples * T / t5, "unit": UNIT, "seconds": t5, "scaling": "strong",
+                "h2d_bytes_rank0": int(4 * 6 * x5.shape[0]), "d2h_bytes_rank0": int(8 * pipe.words + 8 * 3 * Ts),
+                "collectives_per_pass": 2 if world > 1 else 0,
+                "checks": dict(grid_checks(res5), samples_total=opts.config5_samples,
+                               note="integer fingerprints: identical at every --gpus N (same global sample set)")}
+        del x5, r5, res5
+
+    # ---- the fused binning + cost pass alone on the stored slices of the step (K3 inside the pipeline) --------------------
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    one_step()
     reps = 20
     for r in range(reps + 3):
         if r == 3:
             c0.record(stream)
-        _lib.check(L.dp_cost_coll(denv.handle, _lib.ptr(xs), _lib.ptr(ys), 1, 5 * N, _lib.ptr(rho), 1, N, N, Ts, 0,
-                                  _lib.ptr(cost_slices), None, None, None, None, 0, 0, None, sp), "dp_cost_coll")
+        _lib.check(L.dp_pipeline_bin(pipe.handle, _lib.ptr(lmax), _lib.ptr(ibuf), sp), "dp_pipeline_bin")
     c1.record(stream)
     torch.cuda.synchronize(dev)
-    cost_ms = c0.elapsed_time(c1) / reps
-    cost_evals = N * Ts / (cost_ms * 1e-3)
+    bin_ms = c0.elapsed_time(c1) / reps
+    bin_evals = N * Ts / (bin_ms * 1e-3)
+    pipe.close()
+    del pipe, ibuf
 
     # ---- BASELINE config 3: collision cost (forward, forward+backward) and fused binning on 1M weighted samples x 101
     #      time slices of the environment, [t][n] layout, inputs resident in HBM (1.2 GB streamed per pass > L2) -------
     cfg3 = None
     if rank == 0:
-        del x_out, l_out, rho, mass, count
+        spec = _lib.BinSpec()
+        spec.mode = 0
+        spec.geom = G._geom(args)
+        spec.mass_scale_log2 = G.mass_scale_log2(1 << 27, 1.0)
+        cells = (args.grid_size[0] + 1) * (args.grid_size[1] + 1)
         N3, T3 = SAMPLES, 101
         g3 = torch.Generator(device=dev).manual_seed(1)
         tt = torch.linspace(0, 1, T3, device=dev)
@@ -414,7 +470,8 @@ def main():
     #      reference per launch (the reference's call pattern) and 296 references in one launch (dp_rollout_batch) --------
     cfg1 = None
     if rank == 0:
-        n1, T1c, R1 = 20, 1000, 2 * 148
+        flags = _lib.DP_LOG_DENSITY | _lib.DP_DENSITY
+        n1, T1c, R1 = 20, 1000, 6 * 2 * 148
         torch.manual_seed(7)
         refs = []
         while len(refs) < 8:
@@ -437,7 +494,7 @@ def main():
                                           T1c, flags, 1, _lib.ptr(xo1), _lib.ptr(lo1), R1 * n1, None, None, sp), "dp_rollout_batch")
 
         cfg1 = {"workload": "%d samples x %d steps per reference, every step stored (BASELINE config 1 shape)" % (n1, T1c)}
-        for name, fn, work in (("one_reference_per_launch", one_ref, n1 * T1c), ("batched_%d_references" % R1, all_refs, R1 * n1 * T1c)):
+        for name, fn, work in (("one_reference_per_launch", one_ref, n1 * T1c), ("batched", all_refs, R1 * n1 * T1c)):
             fn()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record(stream)
@@ -447,6 +504,7 @@ def main():
             torch.cuda.synchronize(dev)
             ms = a0.elapsed_time(a1) / 3
             cfg1[name] = {"ms": ms, "sample_steps_per_s": work / (ms * 1e-3)}
+        cfg1["batched"]["references_per_launch"] = R1
         del xo1, lo1
 
     if rank != 0:
@@ -454,38 +512,42 @@ def main():
     peaks, peaks_src = measured_peaks()
     tf_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     achieved_tf = N * T * FLOP_PER_SAMPLE_STEP / (k_ms * 1e-3) / 1e12
-    ffma_tf = ctypes.c_double(0)
-    L.dp_probe_ffma_peak(local_rank, ctypes.byref(ffma_tf))
+    executed_tf = N * T * EXECUTED_MMA_FLOP_PER_SAMPLE_STEP / (k_ms * 1e-3) / 1e12
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("rollout_dram_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / tf_peak, "traffic": traffic,
-                "kernel": "rollout (%s)" % (opts.kernel or "default"), "kernel_ms": k_ms,
+                "kernel": "rollout_tc_kernel (tcgen05)", "kernel_ms": k_ms,
                 "peak_source": "%s bf16_tflops_sustained (dense tensor pipe; the rollout is a K=128 dense contraction)" % peaks_src,
                 "algorithmic_flop_per_sample_step": FLOP_PER_SAMPLE_STEP,
-                "fp32_ffma_peak_tflops_measured": ffma_tf.value,
-                "frac_of_fp32_ffma_peak": achieved_tf / ffma_tf.value if ffma_tf.value else None,
-                "hbm_bytes_per_launch_algorithmic": int(4 * Ts * 6 * N + 4 * 5 * N),
-                "cost_kernel": {"bound": "hbm", "evals_per_s": cost_evals, "achieved": 12 * cost_evals / 1e9,
-                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": 12 * cost_evals / 1e9 / peaks["hbm_gbs"],
-                                "bytes_per_eval": 12}}
+                "executed_mma_flop_per_sample_step": EXECUTED_MMA_FLOP_PER_SAMPLE_STEP,
+                "executed_tflops": executed_tf, "frac_executed": executed_tf / tf_peak,
+                "note": "value rows need 3 split-fp16 products for fp32-level accuracy (clip-mask parity), tangent rows 1: the tensor "
+                        "pipe executes 1.69x the algorithmic FLOPs, so frac <= 0.59 x pipe utilisation; frac_executed is the "
+                        "utilisation of the pipe itself",
+                "hbm_bytes_per_launch_algorithmic": int(4 * Ts * 3 * N + 4 * 6 * N),
+                "binning_cost_kernel": {"bound": "hbm", "evals_per_s": bin_evals, "achieved": 12 * bin_evals / 1e9,
+                                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": 12 * bin_evals / 1e9 / peaks["hbm_gbs"],
+                                        "bytes_per_eval": 12, "ms": bin_ms,
+                                        "what": "dp_pipeline_bin on the step's %d stored slices: memset of the 12.9 MB integer "
+                                                "buffer + ONE pass (weights, grids, counts, cost)" % Ts}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": opts.steps, "warmup": max(opts.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "CAR rollout + Liouville density, %d samples x %d steps per GPU (%s), "
-                                   "then normaliser + collision cost + occupancy binning on %d stored slices" % (
-                                       N, T, "BASELINE config 2" if N == SAMPLES else "BASELINE config 5 scale: --samples", Ts),
+            "config": {"workload": "CAR rollout + Liouville density, %d samples x %d steps per GPU (%s), device-resident pipeline: "
+                                   "density weights, occupancy grids and collision cost on %d stored slices" % (
+                                       N, T, "BASELINE config 2" if N == SAMPLES else "--samples", Ts),
                        "samples_per_gpu": N, "horizon_steps": T, "stored_slices": Ts,
                        "controller": "trained C3M controller_CAR_3layers (43,592 fp32 weights)",
-                       "l2_policy": "inputs+outputs per step (%.0f MB written) exceed the 126 MB L2" % (4e-6 * Ts * 6 * N),
-                       "parallelism": "samples sharded, %d rank(s); allreduce of normaliser stats, cost and int grids" % world},
-            "e2e": e2e, "gpu_launches": launches["n"], "clocks": clk, "roofline": roofline,
-            "collision_cost_evals_per_s": cfg3["cost_fwd"]["evals_per_s"] if cfg3 else cost_evals * world,
-            "collision_cost_config3": cfg3, "rawdata_config1": cfg1,
-            "checks": {"grid_count_total": total_count, "grid_mass_total": total_mass, "cost_total": cost_total,
-                       "occupancy_dot_total": float(occ_dot.sum().item())}}
+                       "l2_policy": "inputs+outputs per step (%.0f MB of slices + 13 MB of grids written) exceed the 126 MB L2" % (
+                           4e-6 * Ts * 3 * N),
+                       "parallelism": "samples sharded, %d rank(s); 2 collectives per step (MAX of %d floats, SUM of one int64 "
+                                      "buffer with grids, counts and cost)" % (world, Ts)},
+            "e2e": e2e, "e2e_trajectory": e2e_traj, "config5": cfg5, "gpu_launches": launches["n"], "clocks": clk, "roofline": roofline,
+            "collision_cost_evals_per_s": cfg3["cost_fwd"]["evals_per_s"] if cfg3 else None,
+            "collision_cost_config3": cfg3, "rawdata_config1": cfg1, "checks": checks}
     if not opts.no_cpu_baseline and world == 1:
         base, _, _ = cpu_oracle_rate()
         line["cpu_baseline"] = base

@@ -8,11 +8,11 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdensity_planner_b200.so")
+DIAG_LIB_PATH = os.path.join(_HERE, "libdensity_planner_b200_diag.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 # flags (include/density_planner_b200.h)
 DP_LOG_DENSITY, DP_DENSITY, DP_CUT, DP_ABS_STATE, DP_XY_ONLY = 1, 2, 4, 8, 16
-DP_IMPL_DEFAULT, DP_IMPL_FFMA, DP_IMPL_TC = 0x000, 0x100, 0x200
 DP_CONTROLLER_BLOB_FLOATS = 43592
 
 
@@ -45,6 +45,7 @@ _SIGNATURES = {
     "dp_host_chunk_schedule": (_int, [_i64, _i64, _vp, _int]),
     "dp_step": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dp_pos2gridpos": (_int, [ctypes.POINTER(GridGeom), _vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),
+    "dp_pos2gridpos_f64": (_int, [ctypes.POINTER(GridGeom), _vp, _vp, _i64, _vp, _vp, _vp]),
     "dp_gridpos2pos": (_int, [ctypes.POINTER(GridGeom), _vp, _vp, _i64, _vp, _vp, _vp]),
     "dp_env_create": (_int, [ctypes.POINTER(GridGeom), _int, _vp, _vp, _vp, _int, _int, ctypes.POINTER(_vp)]),
     "dp_env_destroy": (None, [_vp]),
@@ -59,6 +60,20 @@ _SIGNATURES = {
                                  _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
     "dp_normalize_stats": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
     "dp_normalize_apply": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp]),
+    "dp_pipeline_create": (_int, [_vp, _vp, ctypes.POINTER(BinSpec), _int, _int, _i64, _int, ctypes.POINTER(_vp)]),
+    "dp_pipeline_destroy": (None, [_vp]),
+    "dp_pipeline_words": (_int, [_vp, ctypes.POINTER(_i64)]),
+    "dp_pipeline_rollout": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _f32, _i64, _vp, _vp]),
+    "dp_pipeline_bin": (_int, [_vp, _vp, _vp, _vp]),
+    "dp_pipeline_finalize": (_int, [_vp, _vp, _vp, _vp]),
+    "dp_pipeline_copy_slices": (_int, [_vp, _vp, _vp, _vp]),
+    "dp_rollout_fused": (_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp, _vp]),
+}
+
+# diagnostics library (include/density_planner_b200_diag.h): fp32 cross-check rollout + micro-probes, not product ABI
+_DIAG_SIGNATURES = {
+    "dp_diag_last_error": (ctypes.c_char_p, []),
+    "dp_diag_rollout_ffma": (_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _int, _uint, _int, _vp, _vp, _i64, _vp, _vp, _vp]),
     "dp_probe_ffma_peak": (_int, [_int, ctypes.POINTER(ctypes.c_double)]),
     "dp_tc_mma_bench": (_int, [_int, _int, _int, _int, ctypes.POINTER(ctypes.c_double)]),
     "dp_tc_tmem_bench": (_int, [_int, _int, _int, ctypes.POINTER(ctypes.c_double)]),
@@ -66,7 +81,9 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
+DIAG_EXPORTS = tuple(_DIAG_SIGNATURES)
 _lib = None
+_diag = None
 
 
 def build(verbose=False):
@@ -92,6 +109,27 @@ def lib():
             raise DensityPlannerError("ABI version mismatch")
         _lib = L
     return _lib
+
+
+def diag_lib():
+    """The diagnostics library (fp32 cross-check rollout, tcgen05 / TMEM / FFMA probes)."""
+    global _diag
+    if _diag is None:
+        if not os.path.exists(DIAG_LIB_PATH):
+            raise DensityPlannerError("%s not found: build it with `make -C density_planner_b200/csrc`" % DIAG_LIB_PATH)
+        L = ctypes.CDLL(DIAG_LIB_PATH)
+        for name, (res, args) in _DIAG_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _diag = L
+    return _diag
+
+
+def check_diag(rc, what=""):
+    if rc != 0:
+        msg = diag_lib().dp_diag_last_error()
+        raise DensityPlannerError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))
 
 
 def check(rc, what=""):

@@ -1,4 +1,4 @@
-// C ABI glue: error state, controller objects, rollout dispatch, host-buffer entry points, FFMA peak probe.
+// C ABI glue: error state, controller objects, rollout entry points (device and host buffers).
 #include <stdarg.h>
 
 #include <vector>
@@ -102,13 +102,8 @@ int dp_rollout(const dp_controller *c, const float *xe0, const float *xref, cons
     p.big = c->d_big; p.small = c->d_small; p.tc = c->d_tc;
     p.xe0 = xe0; p.xref = xref; p.uref = uref; p.rho0 = rho0;
     p.dt = dt; p.N = N; p.T = T; p.flags = flags; p.stride = stride; p.Ts = T / stride + 1;
-    p.x_out = x_out; p.rho_out = rho_out; p.ldn = ldn; p.clip_margin = clip_margin; p.status = status; p.trace = nullptr; p.R = 1; p.n_per_ref = N; p.T_ref = nullptr;
-    const unsigned impl = flags & DP_IMPL_MASK;
-    // default = the tcgen05 kernel (fp32-level value path); DP_IMPL_FFMA selects the all-fp32 CUDA-core kernel
-    if (impl == DP_IMPL_TC || impl == DP_IMPL_DEFAULT) return dp_launch_rollout_tc(c, p, (cudaStream_t)stream);
-    if (impl == DP_IMPL_FFMA) return dp_launch_rollout_ffma(c, p, (cudaStream_t)stream);
-    dp_set_error("dp_rollout: unknown implementation selector 0x%x", impl);
-    return 2;
+    p.x_out = x_out; p.rho_out = rho_out; p.ldn = ldn; p.clip_margin = clip_margin; p.status = status; p.trace = nullptr; p.R = 1; p.n_per_ref = N; p.T_ref = nullptr; p.lmax_enc = nullptr;
+    return dp_launch_rollout_tc(c, p, (cudaStream_t)stream);  // the tcgen05 kernel: the one rollout backend of this library
 }
 
 int dp_rollout_batch(const dp_controller *c, const float *xe0, const float *xref, const float *uref, const int *T_ref,
@@ -118,8 +113,6 @@ int dp_rollout_batch(const dp_controller *c, const float *xe0, const float *xref
     DP_REQUIRE(T >= 0 && stride >= 1 && R >= 0 && n_per_ref >= 0, "dp_rollout_batch: bad sizes");
     const int64_t N = R * n_per_ref;
     DP_REQUIRE(ldn >= N || (!x_out && !rho_out), "dp_rollout_batch: ldn=%lld < N=%lld", (long long)ldn, (long long)N);
-    const unsigned impl = flags & DP_IMPL_MASK;
-    DP_REQUIRE(impl == DP_IMPL_TC || impl == DP_IMPL_DEFAULT, "dp_rollout_batch: only the tensor-core kernel takes several references");
     if (N <= 0) return 0;
     DeviceGuard guard(c->device);
     RolloutParams p;
@@ -127,7 +120,7 @@ int dp_rollout_batch(const dp_controller *c, const float *xe0, const float *xref
     p.xe0 = xe0; p.xref = xref; p.uref = uref; p.rho0 = rho0;
     p.dt = dt; p.N = N; p.T = T; p.flags = flags; p.stride = stride; p.Ts = T / stride + 1;
     p.x_out = x_out; p.rho_out = rho_out; p.ldn = ldn; p.clip_margin = clip_margin; p.status = status; p.trace = nullptr;
-    p.R = R; p.n_per_ref = n_per_ref; p.T_ref = T_ref;
+    p.R = R; p.n_per_ref = n_per_ref; p.T_ref = T_ref; p.lmax_enc = nullptr;
     return dp_launch_rollout_tc(c, p, (cudaStream_t)stream);
 }
 
@@ -165,6 +158,7 @@ int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const
     DP_REQUIRE(c && xe0 && xref && uref, "dp_rollout_host: null argument");
     DP_REQUIRE(T >= 0 && stride >= 1, "dp_rollout_host: bad T / stride");
     if (N <= 0) return 0;
+    std::lock_guard<std::mutex> lock(c->host_mutex);
     DeviceGuard guard(c->device);
     const int Ts = T / stride + 1;
     const int nd = (flags & DP_XY_ONLY) ? 2 : 5;
@@ -241,54 +235,3 @@ int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const
 }
 
 }  // extern "C"
-
-// ---- FFMA peak probe ---------------------------------------------------------------------------------------------
-namespace {
-__global__ void __launch_bounds__(256) ffma_probe_kernel(float *out, int iters, float a, float b) {
-    float v[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i);
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
-    }
-    float s = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) s += v[i];
-    if (s == 12345.678f) out[0] = s;
-}
-}  // namespace
-
-extern "C" int dp_probe_ffma_peak(int device, double *tflops) {
-    DP_REQUIRE(tflops, "dp_probe_ffma_peak: null argument");
-    DeviceGuard guard(device);
-    cudaDeviceProp prop;
-    DP_CUDA(cudaGetDeviceProperties(&prop, device));
-    float *d;
-    DP_CUDA(cudaMalloc(&d, 4));
-    const int iters = 20000, blocks = prop.multiProcessorCount * 8;
-    cudaEvent_t e0, e1;
-    DP_CUDA(cudaEventCreate(&e0));
-    DP_CUDA(cudaEventCreate(&e1));
-    ffma_probe_kernel<<<blocks, 256>>>(d, 1000, 0.999f, 0.001f);
-    DP_CUDA(cudaDeviceSynchronize());
-    double best = 0;
-    for (int rep = 0; rep < 3; ++rep) {
-        DP_CUDA(cudaEventRecord(e0));
-        ffma_probe_kernel<<<blocks, 256>>>(d, iters, 0.999f, 0.001f);
-        DP_CUDA(cudaEventRecord(e1));
-        DP_CUDA(cudaEventSynchronize(e1));
-        float ms;
-        DP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        const double flops = 2.0 * 128.0 * iters * 256.0 * blocks;
-        const double tf = flops / (ms * 1e-3) / 1e12;
-        if (tf > best) best = tf;
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d);
-    *tflops = best;
-    return 0;
-}

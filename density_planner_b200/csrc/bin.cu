@@ -11,12 +11,13 @@
 // with an integer allreduce).  Optionally the same pass gathers the environment's occupancy of every sample's cell and
 // returns, per slice, sum_s w_s * p[cell_s] = sum_cells mass[cell] * p[cell]: the obstacle-grid dot product of the binned
 // density, without a second pass over the grid.
+#include <stdlib.h>
+
 #include "dp_common.cuh"
 
 namespace {
 
 constexpr int WIN = 80;                  // window edge in cells
-constexpr int BIN_THREADS = 1024;
 constexpr int BIN_SMEM = WIN * WIN * 12 + 64;
 constexpr int MAX_BIN_PARTIALS = 1 << 15;
 
@@ -36,6 +37,14 @@ struct BinArgs {
     int egx, egy;         // its cells per axis
     double *partial;      // [Ts][B] partial occupancy dot products or null
     int B;
+    int agg;              // warp aggregation of same-cell samples before the shared atomics: 0 off, 1 on, 2 decided per block
+    // fused pipeline pass (FUSED kernels, dp_pipeline_bin): the weight column holds the log-density l and the weight is
+    // exp(l - lmax[t]) * rho0[n] (simulation_objects.py:296-297, before the division by the sum); the same pass
+    // accumulates the collision cost of the weighted samples (MotionPlanner.py:206-222) in int64 fixed point
+    const float *lmax;    // [Ts]
+    const float *rho0;    // [N] or null (= 1)
+    long long *cost_q;    // [Ts]
+    float cost_scale_f;
 };
 
 // np.histogramdd bin index for `v` over `bins` uniform bins on [lo, hi] (right edge inclusive); -1 if outside.
@@ -64,17 +73,30 @@ __device__ __forceinline__ void sample_cell(const BinArgs &a, float x, float y, 
     }
 }
 
+// sum of a 64-bit quantity over the lanes of `grp` (a match.any group): three 24-bit limbs through redux.sync
+__device__ __forceinline__ long long group_sum_ll(unsigned grp, long long q) {
+    const unsigned lo = (unsigned)(q & 0xFFFFFF), mid = (unsigned)((q >> 24) & 0xFFFFFF);
+    const int hi = (int)(q >> 48);
+    const unsigned rlo = __reduce_add_sync(grp, lo), rmid = __reduce_add_sync(grp, mid);
+    const int rhi = __reduce_add_sync(grp, hi);
+    return (long long)rlo + ((long long)rmid << 24) + ((long long)rhi << 48);
+}
+
 // The int64 mass of a window cell is kept as two 32-bit words: a native 32-bit shared-memory atomic on the low word returns
 // the old value, which tells exactly whether this addition carried into the high word (a 64-bit shared atomicAdd would
-// be a compare-and-swap loop that degrades under the contention of a tight sample cloud).
-template <int MODE, bool VEC>
-__global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
+// be a compare-and-swap loop that degrades under the contention of a tight sample cloud).  Where many samples of a warp
+// fall into the same cell (tight clouds: the planner's few hundred samples, late slices of a contracting closed loop) the
+// warp first sums them (match.any + redux) and only the group leaders touch shared memory; whether that pays is decided
+// per block from a probe of 32 consecutive samples (agg == 2) -- for a diffuse cloud the match costs more than it saves.
+template <int MODE, bool VEC, bool FUSED, int NT>
+__global__ void __launch_bounds__(NT, 2) bin2d_kernel(BinArgs a) {
     extern __shared__ __align__(16) unsigned char bsm[];
     unsigned *slo = reinterpret_cast<unsigned *>(bsm);
     unsigned *shi = reinterpret_cast<unsigned *>(bsm + WIN * WIN * 4);
     int *scount = reinterpret_cast<int *>(bsm + WIN * WIN * 8);
     int *sorg = reinterpret_cast<int *>(bsm + WIN * WIN * 12);
-    __shared__ double shd[BIN_THREADS / 32];
+    __shared__ double shd[NT / 32];
+    __shared__ long long shq[NT / 32];
     const int t = blockIdx.y, tid = threadIdx.x;
     const float *xp = a.x + (long long)t * a.sx_t;
     const float *yp = a.y + (long long)t * a.sx_t;
@@ -83,11 +105,13 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
     long long *mass = a.mass ? a.mass + (long long)t * cells : nullptr;
     int *count = a.count ? a.count + (long long)t * cells : nullptr;
     const float4 *tab = a.table ? a.table + (size_t)t * a.egx * a.egy : nullptr;
+    const float mx = FUSED ? __ldg(a.lmax + t) : 0.0f;
     // this block's samples: a contiguous chunk of the slice
     long long chunk = (a.N + gridDim.x - 1) / gridDim.x;
     if (VEC) chunk = (chunk + 3) & ~3LL;
     const long long n_lo = min((long long)blockIdx.x * chunk, a.N), n_hi = min(n_lo + chunk, a.N);
-    // window origin: mean cell of 32 probe samples spread over the chunk (any choice gives the same integer grids)
+    // window origin: mean cell of 32 probe samples spread over the chunk (any choice gives the same integer grids); the
+    // same warp looks at 32 consecutive samples to see how many share a cell
     if (tid < 32) {
         int ix = 0, iy = 0, ok = 0;
         if (n_lo < n_hi) {
@@ -102,29 +126,45 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
             sy += __shfl_xor_sync(0xffffffffu, sy, m);
             sk += __shfl_xor_sync(0xffffffffu, sk, m);
         }
+        int use_agg = a.agg == 1;
+        if (a.agg == 2) {
+            int c2 = -1 - tid;  // lanes without a sample never match
+            if (n_lo + tid < n_hi) {
+                int jx, jy;
+                sample_cell<MODE>(a, __ldg(xp + (n_lo + tid) * a.sx_n), __ldg(yp + (n_lo + tid) * a.sx_n), jx, jy);
+                c2 = jx * a.cy + jy;
+            }
+            const unsigned grp = __match_any_sync(0xffffffffu, c2);
+            const unsigned leaders = __ballot_sync(0xffffffffu, (int)(__ffs(grp) - 1) == tid);
+            use_agg = __popc(leaders) <= 20;  // at least 3 of 8 samples ride on another lane's atomic
+        }
         if (tid == 0) {
             const int mx_ = sk ? sx / sk : 0, my_ = sk ? sy / sk : 0;
             sorg[0] = min(max(mx_ - WIN / 2, 0), max(a.cx - WIN, 0));
             sorg[1] = min(max(my_ - WIN / 2, 0), max(a.cy - WIN, 0));
+            sorg[2] = use_agg;
         }
     }
-    for (int i = tid; i < WIN * WIN; i += BIN_THREADS) {
+    for (int i = tid; i < WIN * WIN; i += NT) {
         slo[i] = 0u;
         shi[i] = 0u;
         scount[i] = 0;
     }
     __syncthreads();
     const int ox = sorg[0], oy = sorg[1];
+    const bool agg = sorg[2] != 0;
     double dot = 0.0;
+    long long cq = 0;
     // one sample: window cell -> shared atomics; outside the window -> warp-aggregated global atomics (all lanes take part
     // in the collectives, `live` tells whether this lane carries a sample)
-    auto put = [&](bool live, float x, float y, float w) {
+    auto put = [&](bool live, float x, float y, float w, float r0) {
         int cell = -1, wcell = -1;
         long long q = 0;
         if (live) {
             int ix, iy;
             sample_cell<MODE>(a, x, y, ix, iy);
             if (ix >= 0 && iy >= 0) {
+                if (FUSED) w = __fmul_rn(expf(__fsub_rn(w, mx)), r0);  // simulation_objects.py:296-297
                 // w * 2^s is exact in fp32 (power-of-two scale), so this equals llrint((double)w * 2^s)
                 q = wp ? __float2ll_rn(__fmul_rn(w, a.scale_f)) : (long long)a.scale;
                 const int wx = ix - ox, wy = iy - oy;
@@ -132,10 +172,32 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
                     wcell = wx * WIN + wy;
                 else
                     cell = ix * a.cy + iy;
-                if (tab && ix < a.egx && iy < a.egy) dot += (double)q * (double)__ldg(&tab[(size_t)ix * a.egy + iy].x);
+                if (tab) {
+                    if (FUSED) {
+                        // the cost clamps the cell to [0, G-1] (MotionPlanner.py:208-209), the binning to [0, G]
+                        const int jx = min(ix, a.egx - 1), jy = min(iy, a.egy - 1);
+                        const float4 e = __ldg(tab + (size_t)jx * a.egy + jy);
+                        const DpEval ev = dp_cost_term(e, a.q, jx, jy, x, y, w, true);
+                        cq += __float2ll_rn(__fmul_rn(ev.term, a.cost_scale_f));
+                    } else if (ix < a.egx && iy < a.egy) {
+                        dot += (double)q * (double)__ldg(&tab[(size_t)ix * a.egy + iy].x);
+                    }
+                }
             }
         }
-        if (wcell >= 0) {
+        if (agg) {
+            const unsigned grp = __match_any_sync(0xffffffffu, wcell);
+            const long long qs = group_sum_ll(grp, q);
+            if (wcell >= 0 && (int)(tid & 31) == (int)(__ffs(grp) - 1)) {
+                if (mass) {
+                    const unsigned ql = (unsigned)qs, qh = (unsigned)((unsigned long long)qs >> 32);
+                    const unsigned old = atomicAdd(slo + wcell, ql);
+                    const unsigned carry = (old + ql < old) ? 1u : 0u;
+                    if (qh + carry) atomicAdd(shi + wcell, qh + carry);
+                }
+                if (count) atomicAdd(scount + wcell, __popc(grp));
+            }
+        } else if (wcell >= 0) {
             if (mass) {
                 const unsigned ql = (unsigned)q, qh = (unsigned)((unsigned long long)q >> 32);
                 const unsigned old = atomicAdd(slo + wcell, ql);
@@ -146,13 +208,8 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
         }
         if (__any_sync(0xffffffffu, cell >= 0)) {
             const unsigned grp = __match_any_sync(0xffffffffu, cell);
-            const int leader = __ffs(grp) - 1;
-            const unsigned lo = (unsigned)(q & 0xFFFFFF), mid = (unsigned)((q >> 24) & 0xFFFFFF);
-            const int hi = (int)(q >> 48);
-            const unsigned rlo = __reduce_add_sync(grp, lo), rmid = __reduce_add_sync(grp, mid);
-            const int rhi = __reduce_add_sync(grp, hi);
-            if (cell >= 0 && (int)(tid & 31) == leader) {
-                const long long sum = (long long)rlo + ((long long)rmid << 24) + ((long long)rhi << 48);
+            const long long sum = group_sum_ll(grp, q);
+            if (cell >= 0 && (int)(tid & 31) == (int)(__ffs(grp) - 1)) {
                 if (mass) atomicAdd(reinterpret_cast<unsigned long long *>(mass + cell), (unsigned long long)sum);
                 if (count) atomicAdd(count + cell, __popc(grp));
             }
@@ -164,18 +221,19 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
         // thread and iteration
         const long long g_lo = n_lo >> 2, g_hi = n_hi >> 2;  // full groups of four
         const long long gmax = g_lo + (((g_hi - g_lo) + 31) / 32) * 32;
-        for (long long g = g_lo + tid; g < gmax; g += BIN_THREADS) {
+        for (long long g = g_lo + tid; g < gmax; g += NT) {
             const bool live = g < g_hi;
-            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = xv, wv = xv;
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = xv, wv = xv, rv = make_float4(1.f, 1.f, 1.f, 1.f);
             if (live) {
                 xv = __ldg(reinterpret_cast<const float4 *>(xp) + g);
                 yv = __ldg(reinterpret_cast<const float4 *>(yp) + g);
                 if (wp) wv = __ldg(reinterpret_cast<const float4 *>(wp) + g);
+                if (FUSED && a.rho0) rv = __ldg(reinterpret_cast<const float4 *>(a.rho0) + g);
             }
-            put(live, xv.x, yv.x, wv.x);
-            put(live, xv.y, yv.y, wv.y);
-            put(live, xv.z, yv.z, wv.z);
-            put(live, xv.w, yv.w, wv.w);
+            put(live, xv.x, yv.x, wv.x, rv.x);
+            put(live, xv.y, yv.y, wv.y, rv.y);
+            put(live, xv.z, yv.z, wv.z, rv.z);
+            put(live, xv.w, yv.w, wv.w, rv.w);
         }
         // the last block of the slice also takes the (at most three) samples behind the last full group
         const long long t_lo = g_hi << 2;
@@ -183,20 +241,21 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
         if (tail && __any_sync(0xffffffffu, t_lo + tid < a.N)) {
             const long long n = t_lo + tid;
             const bool live = n < a.N;
-            put(live, live ? __ldg(xp + n) : 0.f, live ? __ldg(yp + n) : 0.f, (live && wp) ? __ldg(wp + n) : 0.f);
+            put(live, live ? __ldg(xp + n) : 0.f, live ? __ldg(yp + n) : 0.f, (live && wp) ? __ldg(wp + n) : 0.f,
+                (FUSED && live && a.rho0) ? __ldg(a.rho0 + n) : 1.f);
         }
     } else {
         const long long nmax = ((span + 31) / 32) * 32;  // keep warps converged for the match/redux collectives
-        for (long long k = tid; k < nmax; k += BIN_THREADS) {
+        for (long long k = tid; k < nmax; k += NT) {
             const long long n = n_lo + k;
             const bool live = k < span;
             put(live, live ? __ldg(xp + n * a.sx_n) : 0.f, live ? __ldg(yp + n * a.sx_n) : 0.f,
-                (live && wp) ? __ldg(wp + n * a.sw_n) : 0.f);
+                (live && wp) ? __ldg(wp + n * a.sw_n) : 0.f, (FUSED && live && a.rho0) ? __ldg(a.rho0 + n) : 1.f);
         }
     }
     __syncthreads();
     // flush the window: one atomic per touched cell
-    for (int i = tid; i < WIN * WIN; i += BIN_THREADS) {
+    for (int i = tid; i < WIN * WIN; i += NT) {
         const int wx = i / WIN, wy = i - wx * WIN;
         const int ix = ox + wx, iy = oy + wy;
         if (ix < a.cx && iy < a.cy) {
@@ -207,14 +266,24 @@ __global__ void __launch_bounds__(BIN_THREADS, 2) bin2d_kernel(BinArgs a) {
             if (count && c) atomicAdd(count + g, c);
         }
     }
-    if (a.partial) {  // fixed-order block reduction of the occupancy dot product
+    if (FUSED) {  // integer sum: exact and independent of the order (one atomic per block)
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) cq += __shfl_xor_sync(0xffffffffu, cq, m);
+        if ((tid & 31) == 0) shq[tid >> 5] = cq;
+        __syncthreads();
+        if (tid == 0) {
+            long long tot = 0;
+            for (int w = 0; w < NT / 32; ++w) tot += shq[w];
+            if (tot) atomicAdd(reinterpret_cast<unsigned long long *>(a.cost_q + t), (unsigned long long)tot);
+        }
+    } else if (a.partial) {  // fixed-order block reduction of the occupancy dot product
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, m);
         if ((tid & 31) == 0) shd[tid >> 5] = dot;
         __syncthreads();
         if (tid == 0) {
             double tot = 0.0;
-            for (int w = 0; w < BIN_THREADS / 32; ++w) tot += shd[w];
+            for (int w = 0; w < NT / 32; ++w) tot += shd[w];
             a.partial[(size_t)t * a.B + blockIdx.x] = tot;
         }
     }
@@ -305,19 +374,66 @@ __global__ void normalize_apply_kernel(const float *__restrict__ rholog, const f
 
 }  // namespace
 
+// tuning / A-B knobs (read once): DP_BIN_THREADS = 1024 (default, 32 registers per thread) or 512 (64 registers),
+// DP_BIN_AGG = 0 (never aggregate), 1 (always), 2 (default: decided per block from a probe)
+static void bin_knobs(int &threads, int &agg) {
+    static int s_threads = 0, s_agg = 2;
+    if (!s_threads) {
+        const char *e = getenv("DP_BIN_THREADS");
+        s_threads = (e && atoi(e) == 512) ? 512 : 1024;
+        const char *g = getenv("DP_BIN_AGG");
+        if (g) s_agg = atoi(g) < 0 ? 0 : (atoi(g) > 2 ? 2 : atoi(g));
+    }
+    threads = s_threads;
+    agg = s_agg;
+}
+
+template <int NT>
+static int bin2d_dispatch(const BinArgs &a, bool vec, bool fused, dim3 grid, cudaStream_t stream) {
+    static bool attr_set_dev[64] = {};
+    int cur_dev = 0;
+    DP_CUDA(cudaGetDevice(&cur_dev));
+    bool &attr_set = attr_set_dev[cur_dev & 63];
+    if (!attr_set) {
+        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0, false, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0, true, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0, false, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0, true, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<1, false, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        attr_set = true;
+    }
+    if (a.mode == 1)
+        bin2d_kernel<1, false, false, NT><<<grid, NT, BIN_SMEM, stream>>>(a);
+    else if (fused && vec)
+        bin2d_kernel<0, true, true, NT><<<grid, NT, BIN_SMEM, stream>>>(a);
+    else if (fused)
+        bin2d_kernel<0, false, true, NT><<<grid, NT, BIN_SMEM, stream>>>(a);
+    else if (vec)
+        bin2d_kernel<0, true, false, NT><<<grid, NT, BIN_SMEM, stream>>>(a);
+    else
+        bin2d_kernel<0, false, false, NT><<<grid, NT, BIN_SMEM, stream>>>(a);
+    DP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// fused == true (dp_pipeline_bin): w holds the log-density, lmax / rho0 / cost_q as in BinArgs
 static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float *x, const float *y, int64_t sx_n, int64_t sx_t,
                         const float *w, int64_t sw_n, int64_t sw_t, int64_t N, int Ts, long long *mass, int *count,
-                        double *occ_dot, cudaStream_t stream) {
+                        double *occ_dot, bool fused, const float *lmax, const float *rho0, long long *cost_q,
+                        int cost_scale_log2, cudaStream_t stream) {
     DP_REQUIRE(spec && x && y && (mass || count || occ_dot), "dp_bin2d: null argument");
     DP_REQUIRE(spec->mode == 0 || spec->mode == 1, "dp_bin2d: mode must be 0 or 1");
     DP_REQUIRE(spec->mass_scale_log2 >= 0 && spec->mass_scale_log2 <= 62, "dp_bin2d: bad mass_scale_log2");
     DP_REQUIRE(!occ_dot || (env && spec->mode == 0), "dp_bin2d_occ: the occupancy dot product needs an environment and mode 0");
     DP_REQUIRE(!occ_dot || Ts <= env->Tg, "dp_bin2d_occ: Ts=%d exceeds the %d time slices of the environment", Ts, occ_dot ? env->Tg : 0);
+    DP_REQUIRE(!fused || (env && spec->mode == 0 && w && lmax && cost_q && Ts <= env->Tg), "dp_pipeline_bin: bad argument");
     if (Ts <= 0) return 0;
     if (N <= 0) {
         if (occ_dot) DP_CUDA(cudaMemsetAsync(occ_dot, 0, sizeof(double) * Ts, stream));
         return 0;
     }
+    int NT, agg;
+    bin_knobs(NT, agg);
     BinArgs a;
     memset(&a, 0, sizeof(a));
     a.mode = spec->mode;
@@ -334,43 +450,33 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
     a.x = x; a.y = y; a.w = w;
     a.sx_n = sx_n; a.sx_t = sx_t; a.sw_n = sw_n; a.sw_t = sw_t; a.N = N; a.Ts = Ts;
     a.mass = mass; a.count = count;
-    // ~2 resident blocks of 1024 threads per SM, every block amortises one window flush over >= 8 samples per thread
-    long long B = (N + BIN_THREADS * 8 - 1) / (BIN_THREADS * 8);
+    a.agg = agg;
+    a.lmax = lmax; a.rho0 = rho0; a.cost_q = cost_q;
+    a.cost_scale_f = (float)ldexp(1.0, cost_scale_log2);
+    // ~2 resident blocks per SM and two waves; every block amortises one window flush over >= 8 samples per thread
+    long long B = (N + NT * 8 - 1) / (NT * 8);
     const long long target = (148LL * 4 + Ts - 1) / Ts;
     if (B > target) B = target;
     if (B * Ts > MAX_BIN_PARTIALS) B = MAX_BIN_PARTIALS / Ts;
     if (B < 1) B = 1;
     a.B = (int)B;
     double *partial = nullptr;
-    if (occ_dot) {
-        DP_REQUIRE(Ts <= MAX_BIN_PARTIALS, "dp_bin2d_occ: too many slices");
-        DP_CUDA(cudaMallocAsync(&partial, sizeof(double) * B * Ts, stream));
+    if (occ_dot || fused) {
         a.table = env->d_table;
         a.egx = env->geom.gx;
         a.egy = env->geom.gy;
+    }
+    if (occ_dot) {
+        DP_REQUIRE(Ts <= MAX_BIN_PARTIALS, "dp_bin2d_occ: too many slices");
+        DP_CUDA(cudaMallocAsync(&partial, sizeof(double) * B * Ts, stream));
         a.partial = partial;
     }
-    static bool attr_set_dev[64] = {};
-    int cur_dev = 0;
-    DP_CUDA(cudaGetDevice(&cur_dev));
-    bool &attr_set = attr_set_dev[cur_dev & 63];
-    if (!attr_set) {
-        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
-        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
-        DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
-        attr_set = true;
-    }
     auto al16 = [](const void *p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
-    const bool vec = a.mode == 0 && sx_n == 1 && (!w || sw_n == 1) && al16(x) && al16(y) && al16(w) && sx_t % 4 == 0 &&
-                     (!w || sw_t % 4 == 0);
+    const bool vec = a.mode == 0 && sx_n == 1 && (!w || sw_n == 1) && al16(x) && al16(y) && al16(w) && al16(rho0) &&
+                     sx_t % 4 == 0 && (!w || sw_t % 4 == 0);
     const dim3 grid((unsigned)B, (unsigned)Ts);
-    if (a.mode == 1)
-        bin2d_kernel<1, false><<<grid, BIN_THREADS, BIN_SMEM, stream>>>(a);
-    else if (vec)
-        bin2d_kernel<0, true><<<grid, BIN_THREADS, BIN_SMEM, stream>>>(a);
-    else
-        bin2d_kernel<0, false><<<grid, BIN_THREADS, BIN_SMEM, stream>>>(a);
-    DP_CUDA(cudaGetLastError());
+    const int rc = NT == 512 ? bin2d_dispatch<512>(a, vec, fused, grid, stream) : bin2d_dispatch<1024>(a, vec, fused, grid, stream);
+    if (rc) return rc;
     if (occ_dot) {
         bin_dot_finalize_kernel<<<(Ts + 127) / 128, 128, 0, stream>>>(partial, a.B, Ts, 1.0 / a.scale, occ_dot);
         DP_CUDA(cudaGetLastError());
@@ -379,10 +485,20 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
     return 0;
 }
 
+// fused pipeline pass (pipeline.cu): weights exp(l - lmax[t]) * rho0[n] formed in the kernel, occupancy grids and the
+// collision cost of the weighted samples (int64 fixed point) from one pass over x, y, l
+int dp_bin2d_fused_launch(const dp_bin_spec *spec, const dp_env *env, const float *x, const float *y, int64_t sx_t,
+                          const float *l, int64_t sl_t, const float *rho0, const float *lmax, int64_t N, int Ts,
+                          long long *mass, int *count, long long *cost_q, int cost_scale_log2, cudaStream_t stream) {
+    return bin2d_launch(spec, env, x, y, 1, sx_t, l, 1, sl_t, N, Ts, mass, count, nullptr, true, lmax, rho0, cost_q,
+                        cost_scale_log2, stream);
+}
+
 int dp_bin2d(const dp_bin_spec *spec, const float *x, const float *y, int64_t sx_n, int64_t sx_t, const float *w,
              int64_t sw_n, int64_t sw_t, int64_t N, int Ts, long long *mass, int *count, void *stream) {
     DP_REQUIRE(mass || count, "dp_bin2d: null argument");
-    return bin2d_launch(spec, nullptr, x, y, sx_n, sx_t, w, sw_n, sw_t, N, Ts, mass, count, nullptr, (cudaStream_t)stream);
+    return bin2d_launch(spec, nullptr, x, y, sx_n, sx_t, w, sw_n, sw_t, N, Ts, mass, count, nullptr, false, nullptr, nullptr,
+                        nullptr, 0, (cudaStream_t)stream);
 }
 
 int dp_bin2d_occ(const dp_bin_spec *spec, const dp_env *env, const float *x, const float *y, int64_t sx_n, int64_t sx_t,
@@ -390,7 +506,8 @@ int dp_bin2d_occ(const dp_bin_spec *spec, const dp_env *env, const float *x, con
                  void *stream) {
     DP_REQUIRE(env && occ_dot, "dp_bin2d_occ: null argument");
     DeviceGuard guard(env->device);
-    return bin2d_launch(spec, env, x, y, sx_n, sx_t, w, sw_n, sw_t, N, Ts, mass, count, occ_dot, (cudaStream_t)stream);
+    return bin2d_launch(spec, env, x, y, sx_n, sx_t, w, sw_n, sw_t, N, Ts, mass, count, occ_dot, false, nullptr, nullptr,
+                        nullptr, 0, (cudaStream_t)stream);
 }
 
 int dp_normalize_stats(const float *rholog, const float *rho0, int64_t N, int Ts, int64_t ldn, float *lmax,

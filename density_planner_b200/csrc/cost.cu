@@ -12,37 +12,9 @@ constexpr int CB = 256;  // threads per block
 constexpr int MAX_PARTIALS = 1 << 16;
 
 typedef DpGeom Geom;
+typedef DpEval Eval;
 #define make_geom dp_make_geom
-
-// one (sample, slice) evaluation.  Returns the fp32 term rho*p*sq (0 if inactive) and optionally the gradients.
-struct Eval {
-    float term, gx, gy, grho;
-    bool active;
-};
-
-__device__ __forceinline__ Eval eval_one(const float4 *__restrict__ table, const Geom &q, int t, float x, float y, float rho,
-                                         bool has_rho) {
-    int ix = dp_cell<false>(x, q.x_lo, q.x_rng, q.r_x_rng, q.gxm1);
-    int iy = dp_cell<false>(y, q.y_lo, q.y_rng, q.r_y_rng, q.gym1);
-    ix = min(max(ix, 0), q.gx - 1);  // :208-209
-    iy = min(max(iy, 0), q.gy - 1);
-    const float4 e = __ldg(table + ((size_t)t * q.gx + ix) * q.gy + iy);  // {p, gradX, gradY, 0}
-    Eval r;
-    r.active = (e.y != 0.0f) || (e.z != 0.0f);  // :213-214
-    // des_gridpos = gridpos + 100 * grad ; gridpos2pos ; squared distance (:215-218), each op rounded like torch
-    const float dgx = __fadd_rn(__int2float_rn(ix), __fmul_rn(100.0f, e.y));
-    const float dgy = __fadd_rn(__int2float_rn(iy), __fmul_rn(100.0f, e.z));
-    const float dpx = dp_pos<false>(dgx, q.x_lo, q.x_rng, q.gxm1, q.r_gxm1);
-    const float dpy = dp_pos<false>(dgy, q.y_lo, q.y_rng, q.gym1, q.r_gym1);
-    const float ex = __fsub_rn(dpx, x), ey = __fsub_rn(dpy, y);
-    const float sq = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
-    const float w = has_rho ? __fmul_rn(rho, e.x) : e.x;
-    r.term = r.active ? __fmul_rn(w, sq) : 0.0f;
-    r.gx = r.active ? __fmul_rn(-2.0f, __fmul_rn(w, ex)) : 0.0f;
-    r.gy = r.active ? __fmul_rn(-2.0f, __fmul_rn(w, ey)) : 0.0f;
-    r.grho = r.active ? __fmul_rn(e.x, sq) : 0.0f;
-    return r;
-}
+#define eval_one dp_cost_eval
 
 __device__ __forceinline__ double block_reduce_sum(double v, double *sh) {
 #pragma unroll
@@ -416,6 +388,15 @@ __global__ void pos2gridpos_kernel(Geom q, const float *px, const float *py, lon
         }
     }
 }
+// float64 inputs (python floats / lists / numpy float64 arrays reach the reference's pos2gridpos as float64 and are
+// evaluated in double precision there, motion_planning/utils.py:79-85): the same ops in fp64, round half to even
+__global__ void pos2gridpos_f64_kernel(double lo_x, double rng_x, double gxm1, double lo_y, double rng_y, double gym1,
+                                       const double *px, const double *py, long long n, long long *ix, long long *iy) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (px) ix[i] = __double2ll_rn(__dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(px[i], lo_x), rng_x), gxm1), 0.001));
+        if (py) iy[i] = __double2ll_rn(__dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(py[i], lo_y), rng_y), gym1), 0.001));
+    }
+}
 __global__ void gridpos2pos_kernel(Geom q, const float *gx, const float *gy, long long n, float *px, float *py) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         if (gx) px[i] = dp_pos(gx[i], q.x_lo, q.x_rng, q.gxm1, q.r_gxm1);
@@ -432,6 +413,21 @@ int dp_pos2gridpos(const dp_grid_geom *g, const float *px, const float *py, int6
     if (blocks > 148 * 32) blocks = 148 * 32;
     pos2gridpos_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(make_geom(*g), px, py, n, ix, iy, clamp_hi_x,
                                                                          clamp_hi_y);
+    DP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int dp_pos2gridpos_f64(const dp_grid_geom *g, const double *px, const double *py, int64_t n, int64_t *ix, int64_t *iy,
+                       void *stream) {
+    DP_REQUIRE(g && (!px || ix) && (!py || iy), "dp_pos2gridpos_f64: bad argument");
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    // the reference subtracts / divides by the python numbers of args.environment_size (ints or floats -> float64)
+    pos2gridpos_f64_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (double)g->x_min, (double)g->x_max - (double)g->x_min, (double)(g->gx - 1), (double)g->y_min,
+        (double)g->y_max - (double)g->y_min, (double)(g->gy - 1), px, py, n, reinterpret_cast<long long *>(ix),
+        reinterpret_cast<long long *>(iy));
     DP_CUDA(cudaGetLastError());
     return 0;
 }

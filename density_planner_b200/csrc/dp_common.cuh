@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/density_planner_b200.h"
 
 #define DP_HID 128
@@ -46,6 +48,7 @@ struct dp_controller {
     cudaStream_t host_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    std::mutex host_mutex;  // the *_host entry points share the workspace and the streams above: one call at a time
 };
 
 struct dp_env {
@@ -110,11 +113,30 @@ struct RolloutParams {
     // optional per-reference horizons T_ref[R] <= T (device); R <= 1: one shared reference
     long long R, n_per_ref;
     const int *T_ref;
+    // optional: per stored slot, the maximum of the stored (log-)density over the samples, as an order-preserving
+    // unsigned image of the float (dp_decode_ordered); zero-initialised by the caller (pipeline.cu)
+    unsigned *lmax_enc;
 };
+
+// order-preserving unsigned image of a float (atomicMax on floats of either sign) and its inverse
+__host__ __device__ inline unsigned dp_encode_ordered(float f) {
+    unsigned b;
+    memcpy(&b, &f, 4);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ inline float dp_decode_ordered(unsigned e) {
+    const unsigned b = (e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
 
 int dp_launch_rollout_ffma(const dp_controller *c, const RolloutParams &p, cudaStream_t stream);
 int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStream_t stream);
 int dp_tc_prepare(dp_controller *c, const float *host_blob);  // builds c->d_tc
+int dp_bin2d_fused_launch(const dp_bin_spec *spec, const dp_env *env, const float *x, const float *y, int64_t sx_t,
+                          const float *l, int64_t sl_t, const float *rho0, const float *lmax, int64_t N, int Ts,
+                          long long *mass, int *count, long long *cost_q, int cost_scale_log2, cudaStream_t stream);
 void dp_tc_release(dp_controller *c);
 
 // ---- small device helpers ----------------------------------------------------------------------------------
@@ -170,4 +192,41 @@ __device__ __forceinline__ int dp_cell(float p, float lo, float range, float r_r
 template <bool GUARD = true>
 __device__ __forceinline__ float dp_pos(float g, float lo, float range, float gm1, float r_gm1) {
     return __fadd_rn(__fmul_rn(GUARD ? dp_div(g, gm1, r_gm1) : dp_div_fast(g, gm1, r_gm1), range), lo);
+}
+
+// one (sample, slice) evaluation of the collision cost (MotionPlanner.get_cost_coll, motion_planning/MotionPlanner.py:206-222;
+// shared by cost.cu and the fused binning pass of bin.cu).  Returns the fp32 term rho*p*sq (0 if inactive) and optionally the gradients.
+struct DpEval {
+    float term, gx, gy, grho;
+    bool active;
+};
+
+// the terms of one evaluation from the gathered table entry e = {p, gradX, gradY, 0} of the (clamped) cell (ix, iy)
+__device__ __forceinline__ DpEval dp_cost_term(const float4 e, const DpGeom &q, int ix, int iy, float x, float y, float rho,
+                                               bool has_rho) {
+    DpEval r;
+    r.active = (e.y != 0.0f) || (e.z != 0.0f);  // :213-214
+    // des_gridpos = gridpos + 100 * grad ; gridpos2pos ; squared distance (:215-218), each op rounded like torch
+    const float dgx = __fadd_rn(__int2float_rn(ix), __fmul_rn(100.0f, e.y));
+    const float dgy = __fadd_rn(__int2float_rn(iy), __fmul_rn(100.0f, e.z));
+    const float dpx = dp_pos<false>(dgx, q.x_lo, q.x_rng, q.gxm1, q.r_gxm1);
+    const float dpy = dp_pos<false>(dgy, q.y_lo, q.y_rng, q.gym1, q.r_gym1);
+    const float ex = __fsub_rn(dpx, x), ey = __fsub_rn(dpy, y);
+    const float sq = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+    const float w = has_rho ? __fmul_rn(rho, e.x) : e.x;
+    r.term = r.active ? __fmul_rn(w, sq) : 0.0f;
+    r.gx = r.active ? __fmul_rn(-2.0f, __fmul_rn(w, ex)) : 0.0f;
+    r.gy = r.active ? __fmul_rn(-2.0f, __fmul_rn(w, ey)) : 0.0f;
+    r.grho = r.active ? __fmul_rn(e.x, sq) : 0.0f;
+    return r;
+}
+
+__device__ __forceinline__ DpEval dp_cost_eval(const float4 *__restrict__ table, const DpGeom &q, int t, float x, float y, float rho,
+                                               bool has_rho) {
+    int ix = dp_cell<false>(x, q.x_lo, q.x_rng, q.r_x_rng, q.gxm1);
+    int iy = dp_cell<false>(y, q.y_lo, q.y_rng, q.r_y_rng, q.gym1);
+    ix = min(max(ix, 0), q.gx - 1);  // :208-209
+    iy = min(max(iy, 0), q.gy - 1);
+    const float4 e = __ldg(table + ((size_t)t * q.gx + ix) * q.gy + iy);  // {p, gradX, gradY, 0}
+    return dp_cost_term(e, q, ix, iy, x, y, rho, has_rho);
 }

@@ -87,8 +87,10 @@ static_assert(SP_B3R + 64 == SMALL_NET_FLOATS, "small block layout");
 constexpr int OFF_Z = IMAGE_BYTES;                              // float [2 groups][36][128]: tz, A, B per z-row
 constexpr int OFF_PART = OFF_Z + NGROUPS * 36 * TILE * 4;       // float [2 groups][2 halves][4][128]
 constexpr int OFF_CB = OFF_PART + NGROUPS * 2 * 4 * TILE * 4;   // float4 [2 groups][2 nets][64 pairs]: {wz_j, wz_j1, cb_j, cb_j1}
-constexpr int OFF_REF = OFF_CB + NGROUPS * 2 * 64 * 16;         // float [2 groups][3 slots][8]: xref[0..4], uref[0..1] of a time index
-constexpr int OFF_BAR = OFF_REF + NGROUPS * 3 * 8 * 4;          // 2 mbarriers + tmem pointer
+constexpr int REF_SLOTS = 4;                                    // ring of reference rows: the slot written in step i (index i + 2)
+                                                                // was last read in step i - 2, two group barriers earlier
+constexpr int OFF_REF = OFF_CB + NGROUPS * 2 * 64 * 16;         // float [2 groups][4 slots][8]: xref[0..4], uref[0..1] of a time index
+constexpr int OFF_BAR = OFF_REF + NGROUPS * REF_SLOTS * 8 * 4;  // 2 mbarriers + tmem pointer
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -684,8 +686,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
         int next_store = 0, slot = 0;
         // The reference of a time index (5 states, 2 inputs) is read by every thread of the group.  L1 has no room next to
         // 224 KB of shared memory, so every global load would be an L2 round trip on the step's critical path: lanes 0..6 of
-        // one warp fetch time index i + 2 with cp.async while step i runs (three slots), everybody reads shared memory.
-        float *sRef = reinterpret_cast<float *>(smem + OFF_REF) + grp * 3 * 8;
+        // one warp fetch time index i + 2 with cp.async while step i runs, everybody reads shared memory.  Four slots: the
+        // slot overwritten in step i held time index i - 2, whose last readers (the Euler step of step i - 2) are two group
+        // barriers back -- with three slots a lagging warp could still be reading uref[i - 1] from it.
+        float *sRef = reinterpret_cast<float *>(smem + OFF_REF) + grp * REF_SLOTS * 8;
         const int gk = tid & (GT - 1);
         const bool fetcher = (gk >> 5) == 1 && lane < 7;  // second warp of the group (the first one issues the MMAs)
         const float *fsrc = lane < 5 ? xref + lane * T1 : uref + (lane - 5) * p.T;
@@ -702,11 +706,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
         group_sync(c.bar_id);
         for (int i = 0;; ++i) {
             if (fetcher && i + 2 <= flim)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sRef + ((i + 2) % 3) * 8 + lane)),
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sRef + ((i + 2) & (REF_SLOTS - 1)) * 8 + lane)),
                              "l"(fsrc + i + 2)
                              : "memory");
-            const float4 rA = *reinterpret_cast<const float4 *>(sRef + (i % 3) * 8);
-            const float4 rB = *reinterpret_cast<const float4 *>(sRef + (i % 3) * 8 + 4);
+            const float4 rA = *reinterpret_cast<const float4 *>(sRef + (i & (REF_SLOTS - 1)) * 8);
+            const float4 rB = *reinterpret_cast<const float4 *>(sRef + (i & (REF_SLOTS - 1)) * 8 + 4);
             const float xr0 = rA.x, xr1 = rA.y, xr2 = rA.z, xr3 = rA.w;
             if (i == next_store) {
                 // stored slice: the owner thread (h == 0) of each sample writes; a warp covers 32 consecutive samples per row
@@ -741,6 +745,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
                         }
                         if (p.rho_out && dens) p.rho_out[(long long)slot * p.ldn + n] = r;
                     }
+                    // per-slot maximum of the stored (log-)density over all samples (the density normaliser's first pass,
+                    // simulation_objects.py:295): order-preserving integer image of the float, one atomicMax per warp
+                    if (p.lmax_enc && dens) {
+                        const unsigned b = __float_as_uint(r);
+                        const unsigned enc = valid ? ((b & 0x80000000u) ? ~b : (b | 0x80000000u)) : 0u;
+                        const unsigned m = __reduce_max_sync(0xffffffffu, enc);
+                        if (lane == 0 && m) atomicMax(p.lmax_enc + slot, m);
+                    }
                 }
                 next_store += p.stride;
                 ++slot;
@@ -748,7 +760,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
             if (i == T) break;
             // the chains take the controller's error state and network input from the sample state and the reference row
             // in shared memory where they need them (nothing but the state stays in registers across a chain)
-            const float *ref = sRef + (i % 3) * 8;
+            const float *ref = sRef + (i & (REF_SLOTS - 1)) * 8;
             float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 1
             for (int net = 0; net < 2; ++net) {  // net a, then net b; the two TMEM regions swap roles
@@ -759,7 +771,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
             // exchange the partial head sums of the two feature halves (fixed order: both threads get identical totals)
             float *mine = sPart + h * 4 * TILE + c.s;
             mine[0 * TILE] = acc[0]; mine[1 * TILE] = acc[1]; mine[2 * TILE] = acc[2]; mine[3 * TILE] = acc[3];
-            if (i + 1 < T) *cb_mine = fmaf(*cb_wp, sRef[((i + 1) % 3) * 8 + 3], *cb_bp);  // every thread is past both L1 stages
+            if (i + 1 < T) *cb_mine = fmaf(*cb_wp, sRef[((i + 1) & (REF_SLOTS - 1)) * 8 + 3], *cb_bp);  // every thread is past both L1 stages
             TRACE(16);
             asm volatile("cp.async.wait_all;" ::: "memory");  // time index i + 2 has landed (it had the whole step)
             fence_before();

@@ -32,30 +32,59 @@ def _cuda_device(t=None):
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def pos2gridpos(args, pos_x=None, pos_y=None):
-    """World -> grid coordinates (motion_planning/utils.py:70-97); int64 tensors on the input's device."""
+def _pos2gridpos_one(args, p, which):
+    """One coordinate of pos2gridpos with the reference's dtype rules (motion_planning/utils.py:79-97):
+    float32 tensors -> fp32 ops (the hot case); python lists are `torch.from_numpy(np.array(list))` there, i.e. float64
+    (or int64) tensors; numpy arrays and python scalars stay numpy (float64 arithmetic) and return numpy ints."""
     L = _lib.lib()
-    outs = []
-    for p, which in ((pos_x, 0), (pos_y, 1)):
-        if p is None:
-            outs.append(None)
-            continue
-        if isinstance(p, (list, tuple, np.ndarray)):
-            p = torch.as_tensor(np.asarray(p, dtype=np.float32))
-        dev = _cuda_device(p)
-        pd = p.detach().to(device=dev, dtype=torch.float32).contiguous()
-        idx = torch.empty(pd.shape, dtype=torch.int32, device=dev)
-        g = _geom(args)
+    as_numpy = False
+    if isinstance(p, list):
+        p = torch.from_numpy(np.array(p))
+    elif not torch.is_tensor(p):
+        as_numpy = True
+        scalar = np.ndim(p) == 0
+        a = np.asarray(p)
+        # numpy: float32 arrays stay float32 next to python ints; everything else is evaluated in float64
+        p = torch.from_numpy(np.ascontiguousarray(a if a.dtype == np.float32 else a.astype(np.float64)).reshape(-1))
+        shape = a.shape
+    dev = _cuda_device(p)
+    g = _geom(args)
+    lo = float(args.environment_size[0 if which == 0 else 2])
+    if p.dtype == torch.float64:
+        pd = p.detach().to(device=dev).contiguous()
+        idx = torch.empty(pd.shape, dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
+            a0, a1 = (_lib.ptr(pd), None) if which == 0 else (None, _lib.ptr(pd))
+            i0, i1 = (_lib.ptr(idx), None) if which == 0 else (None, _lib.ptr(idx))
+            _lib.check(L.dp_pos2gridpos_f64(ctypes.byref(g), a0, a1, pd.numel(), i0, i1, _lib.current_stream(dev)),
+                       "dp_pos2gridpos_f64")
+    else:
+        if not p.dtype.is_floating_point:
+            # integer tensors: (p - lo) stays integer, the division promotes it to float32 (torch true division)
+            pd = (p.detach().to(dev) - int(lo)).to(torch.float32).contiguous()
             if which == 0:
-                rc = L.dp_pos2gridpos(ctypes.byref(g), _lib.ptr(pd), None, pd.numel(), _lib.ptr(idx), None, -1, -1,
-                                      _lib.current_stream(dev))
+                g = _lib.GridGeom(0.0, g.x_max - g.x_min, g.y_min, g.y_max, g.gx, g.gy)
             else:
-                rc = L.dp_pos2gridpos(ctypes.byref(g), None, _lib.ptr(pd), pd.numel(), None, _lib.ptr(idx), -1, -1,
-                                      _lib.current_stream(dev))
-        _lib.check(rc, "dp_pos2gridpos")
-        outs.append(idx.to(device=p.device, dtype=torch.int64))
-    return outs[0], outs[1]
+                g = _lib.GridGeom(g.x_min, g.x_max, 0.0, g.y_max - g.y_min, g.gx, g.gy)
+        else:
+            pd = p.detach().to(device=dev, dtype=torch.float32).contiguous()
+        idx = torch.empty(pd.shape, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            a0, a1 = (_lib.ptr(pd), None) if which == 0 else (None, _lib.ptr(pd))
+            i0, i1 = (_lib.ptr(idx), None) if which == 0 else (None, _lib.ptr(idx))
+            _lib.check(L.dp_pos2gridpos(ctypes.byref(g), a0, a1, pd.numel(), i0, i1, -1, -1, _lib.current_stream(dev)),
+                       "dp_pos2gridpos")
+    if as_numpy:
+        out = idx.cpu().numpy().astype(int)
+        return out.reshape(())[()] if scalar else out.reshape(shape)
+    return idx.to(device=p.device, dtype=torch.int64)
+
+
+def pos2gridpos(args, pos_x=None, pos_y=None):
+    """World -> grid coordinates (motion_planning/utils.py:70-97): int64 tensors on the input's device for tensors and
+    lists, numpy integers for numpy / scalar inputs, evaluated in the input's precision like the reference."""
+    return (None if pos_x is None else _pos2gridpos_one(args, pos_x, 0),
+            None if pos_y is None else _pos2gridpos_one(args, pos_y, 1))
 
 
 def gridpos2pos(args, pos_x=None, pos_y=None):
@@ -261,13 +290,17 @@ class DeviceEnv:
         """From a reference `Environment` object after get_gradient()."""
         return cls(env.grid, env.grid_gradientX, env.grid_gradientY, args, device)
 
+    def close(self):
+        """Release the device table (errors surface here; __del__ only guards against interpreter shutdown)."""
+        if getattr(self, "handle", None):
+            h, self.handle = self.handle, None
+            _lib.lib().dp_env_destroy(h)
+
     def __del__(self):
-        try:
-            if getattr(self, "handle", None):
-                _lib.lib().dp_env_destroy(self.handle)
-                self.handle = None
-        except Exception:
-            pass
+        import sys
+        if sys is None or sys.is_finalizing():
+            return
+        self.close()
 
 
 def _cost_call(denv, x, y, rho, get_max, want_grad, per_sample):
@@ -413,6 +446,10 @@ def state_costs(x_traj, rho_traj, lo5, hi5, goal_xy, get_max=False):
     """Raw goal / bounds terms: returns (terms, flags) with terms = [goal, below-bound part, above-bound part] (float32,
     differentiable w.r.t. x_traj and rho_traj in sum mode) and flags = [any x < lo, any x > hi] over state dims 0..3."""
     dev = _cuda_device(x_traj)
+    if x_traj.dim() != 3 or x_traj.shape[1] != 5:
+        raise ValueError("x_traj must be (N, 5, Ts): the kernels read the five CAR state dimensions (got %s)" % (tuple(x_traj.shape),))
+    if rho_traj.dim() != 3 or rho_traj.shape[1] != 1 or rho_traj.shape[0] != x_traj.shape[0]:
+        raise ValueError("rho_traj must be (N, 1, >=Ts) (got %s)" % (tuple(rho_traj.shape),))
     x = x_traj.to(device=dev, dtype=torch.float32)
     rho = rho_traj.to(device=dev, dtype=torch.float32)
     if rho.shape[2] < x.shape[2]:
@@ -423,7 +460,10 @@ def state_costs(x_traj, rho_traj, lo5, hi5, goal_xy, get_max=False):
 def get_cost_goal(x_traj, rho_traj, xrefN, args, evaluate=False, get_max=False):
     """MotionPlanner.get_cost_goal (motion_planning/MotionPlanner.py:121-147) on the kernels."""
     big = [float("inf")] * 5
-    terms, _ = state_costs(x_traj, rho_traj, [-v for v in big], big, (float(xrefN[0, 0, 0]), float(xrefN[0, 1, 0])), get_max)
+    # the reference weights the LAST state with the LAST density sample, rho_traj[:, 0, -1] (:139-141) -- rho_traj may be
+    # longer than x_traj (the LE branch returns 101 states and 1001 densities), so the goal term is its own one-slice call
+    terms, _ = state_costs(x_traj[:, :, -1:], rho_traj[:, :, -1:], [-v for v in big], big,
+                           (float(xrefN[0, 0, 0]), float(xrefN[0, 1, 0])), get_max)
     cost_goal = terms[0]
     close = cost_goal < args.close2goal_thr
     if not evaluate and not bool(close):

@@ -22,9 +22,12 @@ class DensityNN:
     Plain torch on the caller's device (cuBLAS GEMMs on the GPU; a stock dense MLP, SURVEY section 8f row 2 -- not one of
     the hand-written kernels), differentiable w.r.t. `up` and `xe0` like the reference's branch."""
 
-    def __init__(self, weights=None, device=None):
+    def __init__(self, weights=None, device=None, activation="relu"):
         import os
         import numpy as np
+        if activation not in ("relu", "tanh"):
+            raise _lib.DensityPlannerError("DensityNN mirrors the reference's MLP with relu or tanh (got %r)" % (activation,))
+        self.activation = activation
         if weights is None:
             weights = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "density_nn_default.npz")
         z = np.load(weights) if isinstance(weights, str) else weights
@@ -47,8 +50,12 @@ class DensityNN:
         rows = torch.cat((head.unsqueeze(0).expand(Tn, -1, -1), t.reshape(Tn, 1, 1).expand(-1, N, -1),
                           upf.unsqueeze(0).expand(Tn, -1, -1)), dim=2).reshape(Tn * N, -1)                # (Tn*N, 31)
         x = rows
+        if x.shape[1] != self.W[0].shape[1]:
+            raise _lib.DensityPlannerError("the density NN expects %d inputs per row, the discr10 row layout has %d"
+                                           % (self.W[0].shape[1], x.shape[1]))
+        act = torch.relu if self.activation == "relu" else torch.tanh
         for i in range(len(self.W) - 1):
-            x = torch.relu(torch.addmm(self.b[i], x, self.W[i].t()))
+            x = act(torch.addmm(self.b[i], x, self.W[i].t()))
         y = torch.addmm(self.b[-1], x, self.W[-1].t()).reshape(Tn, N, -1)                                # (Tn, N, 6)
         return y[:, :, :5].permute(1, 2, 0), y[:, :, 5:6].permute(1, 2, 0)
 
@@ -155,10 +162,13 @@ def attach(planner, device=None):
     system = Car(ego.args, device=device)
     nn = None
     model = getattr(ego, "model", None)
-    if model is not None and hasattr(model, "state_dict"):
-        # the ego's own density-NN weights, evaluated for all time points in one batched pass on the GPU
+    mirrored = (getattr(ego.args, "nn_type", "MLP") == "MLP" and getattr(ego.args, "activation", "relu") in ("relu", "tanh")
+                and getattr(ego.args, "input_type", "discr10") in ("discr10", "discr5"))
+    if model is not None and hasattr(model, "state_dict") and mirrored:
+        # the ego's own density-NN weights, evaluated for all time points in one batched pass on the GPU; any other
+        # configuration (LSTM, other input rows) keeps the reference's branch (ref_predict below)
         nn = DensityNN(weights={k: v.detach().cpu().numpy() for k, v in model.state_dict().items()},
-                       device=system.controller.controller.device)
+                       device=system.controller.controller.device, activation=getattr(ego.args, "activation", "relu"))
     pred = EgoPredictor(system, ego.args, ego.xref0, ego.xe0, ego.rho0, density_nn=nn)
     ref_predict = ego.predict_density
 

@@ -225,9 +225,10 @@ class ControlAffineSystem:
         """Closed-loop rollout of N samples with Liouville (log-)density (:409-463) in one fused kernel launch.
 
         xe0 (N,5,1), xref_traj (1,5,T+1), uref_traj (1,2,T), rho0 (N,1,1) or None.
-        Returns (xe_traj (N,5,Ts), rho_traj (N,1,Ts) or None); Ts = T+1 unless `stride` > 1 (extension: store every
-        stride-th step).  `impl` selects the kernel ("ffma" / "tc"); `return_margin` adds the per-sample distance of
-        the raw controller output to the actuator clip (audit of clip-mask flips)."""
+        Returns (xe_traj (N,5,Ts), rho_traj (N,1,Ts) or None) on xe0's device; Ts = T+1 unless `stride` > 1 (extension:
+        store every stride-th step).  `return_margin` adds the per-sample distance of the raw controller output to the
+        actuator clip (audit of clip-mask flips).  `impl="ffma"` evaluates the same rollout with the all-fp32 CUDA-core
+        kernel of the DIAGNOSTICS library (the parity suite's fp32 cross-check; not a product backend)."""
         L = _lib.lib()
         dc = self.controller.controller
         dev = dc.device
@@ -240,14 +241,15 @@ class ControlAffineSystem:
                                            % (xref_traj.shape[2], T))
         flags = (_lib.DP_LOG_DENSITY if log_density else 0) | (_lib.DP_DENSITY if compute_density else 0) | \
                 (_lib.DP_CUT if cutting else 0)
-        flags |= {None: _lib.DP_IMPL_DEFAULT, "ffma": _lib.DP_IMPL_FFMA, "tc": _lib.DP_IMPL_TC}[impl]
+        if impl not in (None, "tc", "ffma"):
+            raise _lib.DensityPlannerError("unknown impl %r" % (impl,))
         Ts = T // stride + 1
         status = None
         if N == 0:
             xe_traj = torch.empty((0, 5, Ts), dtype=torch.float32, device=out_dev)
             rho_traj = torch.empty((0, 1, Ts), dtype=torch.float32, device=out_dev) if compute_density else None
             return (xe_traj, rho_traj, torch.empty(0, device=out_dev)) if return_margin else (xe_traj, rho_traj)
-        if out_dev.type == "cuda":
+        if out_dev.type == "cuda" or impl == "ffma":
             xe0_d = _f32(xe0.reshape(N, 5), dev)
             xref_d = _f32(xref_traj.reshape(5, T + 1), dev)
             uref_d = _f32(uref_traj.reshape(2, T), dev)
@@ -257,11 +259,22 @@ class ControlAffineSystem:
             margin = torch.empty(N, dtype=torch.float32, device=dev) if return_margin else None
             st = torch.zeros(2, dtype=torch.int32, device=dev)
             with torch.cuda.device(dev):
-                _lib.check(L.dp_rollout(dc.handle, _lib.ptr(xe0_d), _lib.ptr(xref_d), _lib.ptr(uref_d), _lib.ptr(rho0_d),
-                                        float(dt), N, T, flags, stride, _lib.ptr(x_out), _lib.ptr(rho_out), N,
-                                        _lib.ptr(margin), _lib.ptr(st), _lib.current_stream(dev)), "dp_rollout")
+                if impl == "ffma":
+                    _lib.check_diag(_lib.diag_lib().dp_diag_rollout_ffma(
+                        dc.handle, _lib.ptr(xe0_d), _lib.ptr(xref_d), _lib.ptr(uref_d), _lib.ptr(rho0_d), float(dt), N, T,
+                        flags, stride, _lib.ptr(x_out), _lib.ptr(rho_out), N, _lib.ptr(margin), _lib.ptr(st),
+                        _lib.current_stream(dev)), "dp_diag_rollout_ffma")
+                else:
+                    _lib.check(L.dp_rollout(dc.handle, _lib.ptr(xe0_d), _lib.ptr(xref_d), _lib.ptr(uref_d), _lib.ptr(rho0_d),
+                                            float(dt), N, T, flags, stride, _lib.ptr(x_out), _lib.ptr(rho_out), N,
+                                            _lib.ptr(margin), _lib.ptr(st), _lib.current_stream(dev)), "dp_rollout")
             if compute_density and cutting:
                 status = st.tolist()
+            # results come back on the device of xe0 (another GPU than the controller's, or the CPU for the cross-check)
+            if x_out.device != out_dev:
+                x_out = x_out.to(out_dev)
+                rho_out = rho_out.to(out_dev) if rho_out is not None else None
+                margin = margin.to(out_dev) if margin is not None else None
         else:
             xe0_h = xe0.detach().reshape(N, 5).to(torch.float32).contiguous()
             xref_h = xref_traj.detach().reshape(5, T + 1).to(torch.float32).contiguous()

@@ -38,16 +38,15 @@ extern "C" {
 #define DP_CUT 4u          /* cutting=True: clamp >1e30 (and <0 if linear), NaN -> 1e30 (:451-462)              */
 #define DP_ABS_STATE 8u    /* store x instead of the error state x - xref (the reference returns x - xref)      */
 #define DP_XY_ONLY 16u     /* store only state dims 0,1 (x_out is [Ts][2][ldn]) -- input of the collision cost  */
-/* kernel selection (bits 8..11); 0 = library default */
-#define DP_IMPL_MASK 0xF00u
-#define DP_IMPL_DEFAULT 0x000u
-#define DP_IMPL_FFMA 0x100u   /* fp32 CUDA-core kernel                                                         */
-#define DP_IMPL_TC 0x200u     /* tcgen05 tensor-core kernel, split-precision operands (fp32-level accuracy)    */
+/* There is ONE rollout backend: the tcgen05 tensor-core kernel (split-precision fp16 operands, fp32-level accuracy).
+ * The all-fp32 CUDA-core cross-check kernel and the micro-probes live in the separate diagnostics library
+ * (include/density_planner_b200_diag.h), not in this ABI. */
 
 /* number of fp32 values in a packed controller blob (see dp_controller_create) */
 #define DP_CONTROLLER_BLOB_FLOATS 43592
 
-typedef struct dp_controller dp_controller; /* immutable once created; shareable between threads */
+typedef struct dp_controller dp_controller; /* weights are immutable once created; the device-pointer calls may share a
+                                             * handle between threads; the *_host calls serialise on its host workspace */
 typedef struct dp_env dp_env;               /* occupancy grid + gradients of one environment, repacked on device */
 
 int dp_abi_version(void);
@@ -87,14 +86,16 @@ int dp_rollout(const dp_controller *c, const float *xe0, const float *xref, cons
  *   xe0 dev [R*n_per_ref][5];  xref dev [R][5][T+1];  uref dev [R][2][T] (rows padded to the common T)
  *   T_ref dev int[R] or NULL: horizon of every reference (<= T; slots beyond it are left untouched)
  *   outputs as dp_rollout with N = R*n_per_ref samples, reference r owning samples [r*n_per_ref, (r+1)*n_per_ref)
- * Tensor-core kernel only (every 128-sample tile belongs to one reference).
+ * Samples of several references share a 128-lane tile (the reference is a per-lane property), so R references of 20
+ * samples fill the lanes as R*20 samples of one reference would.
  */
 int dp_rollout_batch(const dp_controller *c, const float *xe0, const float *xref, const float *uref, const int *T_ref,
                      const float *rho0, float dt, int64_t R, int64_t n_per_ref, int T, unsigned flags, int stride,
                      float *x_out, float *rho_out, int64_t ldn, float *clip_margin, int *status, void *stream);
 
 /* Same with HOST buffers (x_out/rho_out host, ld = N); status is a host int[2].  Copies are part of the call: the samples
- * are processed in chunks and the device->host copy of chunk k overlaps the rollout of chunk k+1. */
+ * are processed in chunks and the device->host copy of chunk k overlaps the rollout of chunk k+1.  Thread safe on a shared
+ * controller: concurrent calls serialise on the controller's grow-only device workspace. */
 int dp_rollout_host(dp_controller *c, const float *xe0, const float *xref, const float *uref, const float *rho0,
                     float dt, int64_t N, int T, unsigned flags, int stride, float *x_out, float *rho_out,
                     float *clip_margin, int *status);
@@ -123,6 +124,10 @@ typedef struct dp_grid_geom {
  * px, py dev [n] -> ix, iy dev int32 [n] (either pair may be NULL).  clamp_hi < 0: no clamp, else clamp to [0,clamp] */
 int dp_pos2gridpos(const dp_grid_geom *g, const float *px, const float *py, int64_t n, int32_t *ix, int32_t *iy,
                    int clamp_hi_x, int clamp_hi_y, void *stream);
+/* The same for float64 positions (python floats, lists and numpy float64 arrays are evaluated in double precision by the
+ * reference, :79-85): px, py dev double[n] -> ix, iy dev int64[n], no clamp */
+int dp_pos2gridpos_f64(const dp_grid_geom *g, const double *px, const double *py, int64_t n, int64_t *ix, int64_t *iy,
+                       void *stream);
 /* gridpos2pos (motion_planning/utils.py:100-116) on float grid positions */
 int dp_gridpos2pos(const dp_grid_geom *g, const float *gx, const float *gy, int64_t n, float *px, float *py,
                    void *stream);
@@ -162,8 +167,7 @@ int dp_cost_coll(const dp_env *e, const float *x, const float *y, int64_t sx_n, 
  *   w      dev weights (same addressing as x with sw_n, sw_t) or NULL (weight 1)
  *   mass   dev int64 [Ts][cells]: sum of llrint(w * 2^mass_scale_log2)  (shared-memory window + atomics: exact, order-free)
  *   count  dev int32 [Ts][cells]
- *   occ, occ_cost: if occ != NULL (dev float [cells][To] reference-layout occupancy grid is NOT used here; see
- *          dp_cost_coll) -- reserved, pass NULL.
+ * Either of mass / count may be NULL.  The caller zeroes the grids (the call accumulates into them).
  */
 typedef struct dp_bin_spec {
     int mode;            /* 0 grid cells, 1 uniform bins */
@@ -229,23 +233,54 @@ int dp_cost_state_bwd(const float *x, int64_t sx_n, int64_t sx_d, int64_t sx_t, 
                       float s_hi, float *gx, int64_t sg_n, int64_t sg_d, int64_t sg_t, float *grho, int64_t sgr_n,
                       int64_t sgr_t, void *stream);
 
-/* Diagnostic: one 128 x n x 128 product through the TMEM-operand tcgen05.mma path of the tensor-core rollout
- * (split-precision fp16 operands).  A host fp32 [128][128], W host fp32 [n_valid][128] zero-padded to n rows
- * (n in {128, 48, 32}), mode 0 = value path (3 products), 1 = fp16 activations x (hi + lo) weights (2 products); D host fp32 [128][n]
- * receives A * (scale * W)^T. */
-int dp_tc_selftest(int device, const float *A, const float *W, int n_valid, int n, int mode, float scale, float *D);
+/*
+ * Device-resident pipeline (north-star data flow): sampled initial states -> closed-loop rollout with Liouville log-density
+ * -> density weights -> time-sliced occupancy grids + collision cost, with the trajectories never leaving the GPU.
+ * Replaces the chain  EgoVehicle.predict_density (LE branch + normaliser, motion_planning/simulation_objects.py:288-299)
+ * -> pred2grid per slice (motion_planning/utils.py:255-280) / MotionPlanner.get_cost_coll (motion_planning/MotionPlanner.py:
+ * 192-224) / check_collision (motion_planning/utils.py:231-252).
+ *
+ * The weight of sample n in slice t is the normaliser's NUMERATOR  w = exp(l[t][n] - max_n l[t][.]) * rho0[n]
+ * (simulation_objects.py:296-297); the denominator is the sum of the mass grid, applied in dp_pipeline_finalize.  All
+ * accumulators are integers, so the result buffer is bit-identical for any execution order and any sharding of the
+ * samples over GPUs: a multi-GPU caller needs one MAX allreduce of lmax[Ts] between phases 1 and 2 and one SUM allreduce
+ * of the int64 buffer between phases 2 and 3.
+ *
+ * Integer result buffer (int64 words, dp_pipeline_words), cells = (gx+1)*(gy+1), gc = Ts*cells:
+ *     [0, gc)                        int64 mass[Ts][cells]   = sum of llrint(w * 2^spec.mass_scale_log2)
+ *     [gc, gc + (gc+1)/2)            int32 count[Ts][cells]  (two counts per word; counts are non-negative and their global
+ *                                                            sum is < 2^31, so a 64-bit SUM never carries between them)
+ *     [gc + (gc+1)/2, ... + Ts)      int64 cost[Ts]          = sum of llrint(w * p(cell) * |des(cell) - pos|^2 * 2^cost_scale_log2)
+ */
+typedef struct dp_pipeline dp_pipeline;
 
-/* Diagnostic: cycles per tcgen05.mma (M=128, N=n, K=16, fp16 operands, fp32 accumulate) over 4*iters back-to-back
- * instructions on one SM.  variant 0: A in TMEM + B no-swizzle (the rollout's configuration), 1: A in TMEM + B
- * SWIZZLE_128B, 2: A and B in shared memory no swizzle, 3: both SWIZZLE_128B.  out[0] issue, out[1] completion. */
-int dp_tc_mma_bench(int device, int variant, int n, int iters, double *out);
+/* capacity = most samples one call may carry (device memory: (24 + 12*Ts) bytes per sample); T, stride as in dp_rollout;
+ * spec: mode 0, its mass_scale_log2 must come from DECLARED global bounds (total samples over all GPUs, largest rho0) so
+ * that every shard uses the same fixed point; the controller and the environment must outlive the pipeline. */
+int dp_pipeline_create(const dp_controller *c, const dp_env *env, const dp_bin_spec *spec, int T, int stride, int64_t capacity,
+                       int cost_scale_log2, dp_pipeline **out);
+void dp_pipeline_destroy(dp_pipeline *p);
+int dp_pipeline_words(const dp_pipeline *p, int64_t *words);
 
-/* Diagnostic: cycles per warp-level tcgen05.ld (mode 0) / tcgen05.st (mode 1) / dependent ld+st pair (mode 2) of shape
- * 32x32b.x16 (2 KB per warp) while all 16 warps of one 512-thread CTA issue them: the TMEM bandwidth the epilogues see. */
-int dp_tc_tmem_bench(int device, int mode, int iters, double *cycles_per_op);
+/* Phase 1.  xe0 [N][5], rho0 [N] or NULL (= 1), xref [5][T+1], uref [2][T]: host pointers if inputs_on_host (copied in on
+ * `stream`), else device pointers.  lmax_dev: dev float[Ts] receives the per-slice max of the log-density over THIS shard
+ * (-inf for an empty shard).  Asynchronous on `stream`. */
+int dp_pipeline_rollout(dp_pipeline *p, const float *xe0, const float *rho0, const float *xref, const float *uref,
+                        int inputs_on_host, float dt, int64_t N, float *lmax_dev, void *stream);
+/* Phase 2.  lmax_dev: the GLOBAL per-slice max.  ibuf_dev: dev int64[dp_pipeline_words], zeroed and filled by the call. */
+int dp_pipeline_bin(dp_pipeline *p, const float *lmax_dev, int64_t *ibuf_dev, void *stream);
+/* Phase 3.  From the (summed) integer buffer: out3_dev dev double[3][Ts] = per slice {sum of weights,
+ * collision cost of the normalised density (get_cost_coll's slice term), occupancy dot product of the normalised density
+ * sum_s rho_s * p[cell_s] (what check_collision thresholds)}. */
+int dp_pipeline_finalize(const dp_pipeline *p, const int64_t *ibuf_dev, double *out3_dev, void *stream);
+/* Copies the stored slices of the last dp_pipeline_rollout (N samples) into caller buffers (either may be NULL):
+ * xy_dev dev float[Ts][2][N] absolute positions, l_dev dev float[Ts][N] log-density. */
+int dp_pipeline_copy_slices(const dp_pipeline *p, float *xy_dev, float *l_dev, void *stream);
 
-/* FP32 FFMA peak probe (measures the CUDA-core roofline the fp32 kernel is bounded by); returns TFLOP/s in *tflops */
-int dp_probe_ffma_peak(int device, double *tflops);
+/* All three phases for ONE GPU with HOST buffers (copies inside the call, synchronises before returning):
+ * ibuf_host int64[dp_pipeline_words] or NULL, out3_host double[3][Ts]. */
+int dp_rollout_fused(dp_pipeline *p, const float *xe0, const float *rho0, const float *xref, const float *uref, float dt,
+                     int64_t N, int64_t *ibuf_host, double *out3_host);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,8 @@
 import ctypes, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import density_planner_b200 as dp
-L = dp.lib()
+from density_planner_b200 import _lib as _dl
+L = _dl.diag_lib()
 out = (ctypes.c_double * 2)()
 for variant in (0, 1, 2, 3):
     for n in (32, 48, 64, 128, 256):

@@ -21,7 +21,8 @@ def split16(x):
 def stage_selftest():
     import numpy as np
     import density_planner_b200 as dp
-    L = dp.lib()
+    from density_planner_b200 import _lib as _dl
+    L = _dl.diag_lib()
     rs = np.random.RandomState(0)
     ok = True
     for n, n_valid in ((128, 128), (48, 48), (32, 24)):

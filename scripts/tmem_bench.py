@@ -3,7 +3,8 @@
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import density_planner_b200 as dp
-L = dp.lib()
+from density_planner_b200 import _lib as _dl
+L = _dl.diag_lib()
 for mode, name in ((0, "tcgen05.ld x16"), (1, "tcgen05.st x16"), (2, "ld -> st pair")):
     c = ctypes.c_double(0)
     assert L.dp_tc_tmem_bench(0, mode, 2000, ctypes.byref(c)) == 0

@@ -11,8 +11,8 @@ import torch
 from conftest import ROOT, golden
 
 
-def header_functions():
-    src = open(os.path.join(ROOT, "include", "density_planner_b200.h")).read()
+def header_functions(name="density_planner_b200.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(dp_[a-z0-9_]+)\s*\(", src)))
 
@@ -27,6 +27,21 @@ def test_library_exports_every_declared_symbol(dp):
     # the binding table covers the header too
     assert set(names) == set(_lib.EXPORTS)
     assert dp.lib().dp_abi_version() == 1
+
+
+def test_diagnostics_library_is_separate(dp):
+    """The fp32 cross-check rollout and the micro-probes live in their own library and header, not in the product ABI."""
+    from density_planner_b200 import _lib
+    names = [n for n in header_functions("density_planner_b200_diag.h")]
+    assert set(names) == set(_lib.DIAG_EXPORTS)
+    D = ctypes.CDLL(_lib.DIAG_LIB_PATH)
+    for n in names:
+        assert hasattr(D, n), "missing diagnostics export %s" % n
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert not hasattr(L, n), "%s must not be exported by the product library" % n
+    product = open(os.path.join(ROOT, "include", "density_planner_b200.h")).read()
+    assert "DP_IMPL_FFMA" not in product and "dp_tc_selftest" not in product
 
 
 def test_host_chunk_schedule(dp):

@@ -84,3 +84,67 @@ def test_shard_range_covers_everything():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _pipeline_worker(rank, world, port, q):
+    """The two collectives of the device-resident pipeline (density_planner_b200/pipeline.py) on emulated shard results:
+    MAX of the per-slice log-density maxima, then ONE SUM over the packed int64 buffer (mass | int32 count pairs | cost)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from density_planner_b200 import dist as D
+    import dp_oracle as O
+    D.init_from_env(backend="gloo")
+    rs = np.random.RandomState(1)
+    N, Ts, cx, cy = 4001, 3, 242, 402
+    l = rs.normal(0, 20, (Ts, N)).astype(np.float32)
+    rho0 = rs.uniform(0.5, 1.5, N).astype(np.float32)
+    x = rs.normal(0, 1.5, (Ts, N)).astype(np.float32)
+    y = rs.normal(-10, 3, (Ts, N)).astype(np.float32)
+    term = rs.uniform(0, 30, (Ts, N)).astype(np.float32)  # stands for p * |des - pos|^2 of the sample's cell
+    ks, kc = 34, 20
+
+    def shard_buffer(sl, lmax):
+        gc = Ts * cx * cy
+        buf = np.zeros(gc + (gc + 1) // 2 + Ts, np.int64)
+        mass = buf[:gc].reshape(Ts, cx, cy)
+        count = buf[gc:gc + (gc + 1) // 2].view(np.int32)[:gc].reshape(Ts, cx, cy)
+        cost = buf[gc + (gc + 1) // 2:]
+        for t in range(Ts):
+            w = (np.exp((l[t, sl] - lmax[t]).astype(np.float32)).astype(np.float32) * rho0[sl]).astype(np.float32)
+            gx, gy = O.pos2gridpos(x[t, sl], y[t, sl])
+            gx, gy = np.clip(gx, 0, cx - 1), np.clip(gy, 0, cy - 1)
+            np.add.at(mass[t], (gx, gy), np.rint(w.astype(np.float64) * 2.0 ** ks).astype(np.int64))
+            np.add.at(count[t], (gx, gy), 1)
+            cost[t] = np.rint((w * term[t, sl]).astype(np.float32).astype(np.float64) * 2.0 ** kc).astype(np.int64).sum()
+        return buf
+
+    lo, hi = D.shard_range(N, rank, world)
+    lmax = torch.from_numpy(l[:, lo:hi].max(axis=1))
+    dist.all_reduce(lmax, op=dist.ReduceOp.MAX)
+    ok_max = bool((lmax.numpy() == l.max(axis=1)).all())
+    buf = torch.from_numpy(shard_buffer(slice(lo, hi), lmax.numpy()))
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    full = shard_buffer(slice(0, N), l.max(axis=1))
+    ok_buf = bool((buf.numpy() == full).all())
+    q.put((rank, ok_max, ok_buf))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipeline_collectives_world2_gloo():
+    """Sharded pipeline result == single-process result, bit for bit: integer accumulators, a global max before the
+    weights are quantised, int32 counts summed pairwise inside int64 words without carries."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert r[1] and r[2], r

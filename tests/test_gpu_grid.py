@@ -225,18 +225,33 @@ def test_normalizer_and_planner_le_call(dp, car, oracle, blob, args):
     ref = e["le_rho"]
     got = rho_traj[:, 0, :].numpy()
     big = ref > 1e-6
-    # the normalised density is exp(l - max l) rho0 / sum: a relative error of rho is an ABSOLUTE error of the
-    # log-density l, whose contract is rtol 1e-3 (+1e-4) on |l|; |l| reaches ~40 over these 1000 steps.  The oracle
-    # (pinned to the reference at 8e-7 rel) supplies l; factor 2 for the shift of the normaliser itself.
+    # The normalised density is rho_s = exp(l_s) rho0_s / sum_j exp(l_j) rho0_j, so
+    #     d(log rho_s) = d(l_s) - sum_j rho_j d(l_j):
+    # an error of the log-density l (contract: rtol 1e-3 + 1e-4 on |l|, |l| reaches ~40 over these 1000 steps) moves log rho
+    # by the sample's own error plus the DENSITY-WEIGHTED MEAN of everybody's error (the shift of the normaliser).  The bound
+    # below is that first-order propagation of the contract, per sample and time index -- no slack factor.  The oracle
+    # (pinned to the reference at 8e-7 rel) supplies l.
     uref_long, _ = car.sample_uref_traj(args, up=up)
     xref_long = car.compute_xref_traj(xref0, uref_long, args)
     o_rho = oracle.rollout(blob, e["le_xe0"], xref_long[0].numpy(), uref_long[0].numpy(), args.dt_sim, cutting=False)[1]
-    tol = 2 * (RHO_RTOL * np.abs(o_rho).max(axis=0) + RHO_ATOL)   # per time index
+    tol_l = RHO_RTOL * np.abs(o_rho) + RHO_ATOL                      # (N, 1001): the contract on l
+    tol = tol_l + (ref * tol_l).sum(axis=0, keepdims=True)            # + normaliser shift (ref sums to 1 per time index)
     err = np.abs(np.log(got.clip(1e-30)) - np.log(ref.clip(1e-30)))
-    assert (err <= tol[None, :])[big].all(), "normalised density: max log error %.3g (tol %.3g)" % (err[big].max(), tol.max())
+    assert (err <= tol)[big].all(), "normalised density: max log error %.3g (tol %.3g)" % (err[big].max(), tol[big].max())
     assert np.abs(got.sum(axis=0) - 1).max() < 1e-4
-    # and the cost the planner computes from it
+    # and the cost the planner computes from it.  (a) on IDENTICAL inputs (the reference's own x_traj and rho_traj) the
+    # contract's 1e-4 holds; (b) end to end the cost inherits the density's deviation: it is linear in rho, so the bound is
+    # the tolerance-weighted sum of the per-sample terms -- asserted, and the measured deviation is far inside it (< 2e-3)
     gx, gy = oracle.env_gradient(e["grid"])
     cc = dp.CollisionCost(torch.from_numpy(e["grid"]), torch.from_numpy(gx), torch.from_numpy(gy), args)
+    x_ref5 = torch.zeros(500, 5, 101)
+    x_ref5[:, :2, :] = torch.from_numpy(e["le_x"])
+    c_same = cc.get_cost_coll(x_ref5, torch.from_numpy(ref).unsqueeze(1))
+    assert abs(float(c_same) - e["le_cost"][0]) <= COST_RTOL * abs(e["le_cost"][0])
     c = cc.get_cost_coll(x_traj, rho_traj)
-    assert abs(float(c) - e["le_cost"][0]) <= 2e-3 * abs(e["le_cost"][0])
+    xs, ys = x_ref5[:, 0, :].numpy(), x_ref5[:, 1, :].numpy()
+    _, _, _, odr = oracle.cost_coll(xs, ys, ref[:, :101].copy(), e["grid"], gx, gy, want_grad=True)   # d cost / d rho = p * sq
+    bound = float((np.abs(odr) * ref[:, :101] * np.expm1(tol[:, :101])).sum()) + COST_RTOL * abs(e["le_cost"][0])
+    dev = abs(float(c) - e["le_cost"][0])
+    print("LE cost end to end: deviation %.3g rel, propagated contract bound %.3g rel" % (dev / abs(e["le_cost"][0]), bound / abs(e["le_cost"][0])))
+    assert dev <= bound and dev <= 2e-3 * abs(e["le_cost"][0])

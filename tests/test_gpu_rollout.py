@@ -23,7 +23,8 @@ def test_tc_mma_building_block(dp, n, n_valid, mode):
     """One 128 x n x 128 product through the TMEM-operand tcgen05.mma path against a numpy emulation of the split
     fp16 operands (value path: 3 products, fp32-level; tangent path: fp16 activations x hi+lo weights)."""
     import ctypes
-    L = dp.lib()
+    from density_planner_b200 import _lib
+    L = _lib.diag_lib()
     rs = np.random.RandomState(n + mode)
     A = rs.uniform(-1, 1, (128, 128)).astype(np.float32)
     W = rs.uniform(-0.25, 0.25, (n_valid, 128)).astype(np.float32)
@@ -224,6 +225,25 @@ def test_step_api_vs_reference_golden(car):
     assert np.allclose(rln[safe], g["rholog_next"][safe], rtol=1e-4, atol=1e-5)
 
 
+def _check_rawdata_against_golden(car, args, res, g):
+    """Elementwise contract tolerances (states rtol 1e-4, log-density rtol 1e-3 + clip-flip audit) for the raw-data entries.
+    The clip margins come from replaying the seeded RNG order of compute_data (reference, initial errors, time-index draw:
+    compute_rawdata.py:26-36) and rolling the same samples out once more with return_margin=True."""
+    torch.manual_seed(5)
+    k = args.factor_pred
+    for i, r in enumerate(res):
+        up, uref, xref = car.get_valid_ref(args)
+        xe0 = car.sample_xe0(20)
+        torch.randint(0, xref[:, :, ::k].shape[2], (10,))          # the time-index draw consumes the RNG
+        assert (xe0[:, :, 0].numpy() == g["r%d_xe0" % i]).all()
+        xe, rho, margin = car.compute_density(xe0.cuda(), xref, uref, args.dt_sim, log_density=True, return_margin=True)
+        idx = np.rint(r["t"].numpy() / (args.dt_sim * k)).astype(int)
+        assert bool((xe.cpu()[:, :, ::k][:, :, idx] == r["xe_traj"]).all())    # compute_data returned this very rollout
+        assert_states_close(r["xe_traj"].numpy(), g["r%d_xe_traj" % i], xref[0].numpy()[:, ::k][:, idx], "compute_data[%d]" % i)
+        assert_rho_close(r["rholog_traj"][:, 0, :].numpy(), g["r%d_rholog_traj" % i][:, 0, :], margin.cpu().numpy(),
+                         "compute_data[%d]" % i)
+
+
 def test_compute_data_matches_reference_golden(dp, car, args):
     """data_generation/compute_rawdata.py:9 with seed 5: same references, same samples, same time indices."""
     g = golden("compute_data.npz")
@@ -235,9 +255,7 @@ def test_compute_data_matches_reference_golden(dp, car, args):
         assert (r["xref0"].numpy() == g["r%d_xref0" % i]).all()
         assert (r["t"].numpy() == g["r%d_t" % i]).all()
         assert (r["xe0"].numpy() == g["r%d_xe0" % i]).all()
-        assert np.abs(r["xe_traj"].numpy() - g["r%d_xe_traj" % i]).max() < 1e-4
-        ref = g["r%d_rholog_traj" % i]
-        assert np.abs(r["rholog_traj"].numpy() - ref).max() < 1e-3 * np.abs(ref).max() + 1e-4
+    _check_rawdata_against_golden(car, args, res, g)
 
 
 def test_batched_references_equal_single_launches(dp, car, args):
@@ -269,6 +287,4 @@ def test_compute_data_batched_matches_reference_golden(dp, car, args):
         assert (r["xref0"].numpy() == g["r%d_xref0" % i]).all()
         assert (r["t"].numpy() == g["r%d_t" % i]).all()
         assert (r["xe0"].numpy() == g["r%d_xe0" % i]).all()
-        assert np.abs(r["xe_traj"].numpy() - g["r%d_xe_traj" % i]).max() < 1e-4
-        ref = g["r%d_rholog_traj" % i]
-        assert np.abs(r["rholog_traj"].numpy() - ref).max() < 1e-3 * np.abs(ref).max() + 1e-4
+    _check_rawdata_against_golden(car, args, res, g)
