@@ -43,6 +43,7 @@ struct dp_controller {
     void *d_tc = nullptr;
     size_t tc_bytes = 0;
     bool tc_l2_bounded = false;  // layer-2 pre-activations provably small enough for the sign-free tanh (rollout_tc.cu)
+    float tc_l2_bound = 0.0f;    // the bound itself (scaled pre-activation units)
     // grow-only device workspace + stream for the *_host entry points
     dp_workspace ws;
     cudaStream_t host_stream = nullptr;

@@ -69,6 +69,9 @@ constexpr int NTHREADS = NGROUPS * GT;
 #endif
 constexpr int ISSUER_M1 = DP_ISSUERS / 10000 % 10, ISSUER_M4 = DP_ISSUERS / 1000 % 10, ISSUER_M2 = DP_ISSUERS / 100 % 10,
               ISSUER_M3 = DP_ISSUERS / 10 % 10, ISSUER_M56 = DP_ISSUERS % 10;
+// V (template parameter, bit set): 1 = layer 1 hands r = (1 + h1) / 2 = 1 / (1 + 2^-y) to layer 2 (no |y|, no sign copy, no
+// 2 r - 1; a per-step bound of the pre-activations decides per warp whether the shared reciprocal is safe, else the general
+// tanh is evaluated and converted); 2 = the sign-free evaluations share one reciprocal per PAIR instead of per four.
 // kernel variants (template parameters): TP = tangent products (2: fp16 tangent activations x (hi + lo) weights; 1: hi
 // weights only, the default), KC = K-chunked MMA issue of M1 and M4 (0 off, 1 on: the default), BATCH = several references
 // per launch (dp_rollout_batch), TR = in-kernel clock64 timeline (DP_TC_TRACE)
@@ -81,7 +84,13 @@ constexpr int SP_B3 = 768;   // [64]
 constexpr int SP_C0H = 832;  // [64] half2 pairs of W1[:,0]  (tangent seed d/dtheta)
 constexpr int SP_C1H = 896;  // [64] half2 pairs of W1[:,1]  (tangent seed d/dv)
 constexpr int SP_B3R = 960;  // [64] b3 - rowsum(W3): the layer-3 bias when layer 3 is fed r = (1 + h2) / 2 (SG kernels)
-static_assert(SP_B3R + 64 == SMALL_NET_FLOATS, "small block layout");
+constexpr int SP_B2R = 1024; // [128] (b2 - rowsum(W2)) * 2 log2(e): the layer-2 bias when layer 2 is fed r = (1 + h1) / 2 (V & 1)
+constexpr int SP_C0H4 = 1152; // [64] half2 pairs of 4 W1[:,0]: tangent seed from the parked gate r (1 - r) = (1 - h1^2) / 4
+constexpr int SP_C1H4 = 1216; // [64] half2 pairs of 4 W1[:,1]
+static_assert(SP_C1H4 + 64 == SMALL_NET_FLOATS, "small block layout");
+// bound of every scaled layer-1 pre-activation |y_j| <= BND0 |theta| + BND1 |v| + BND2 |in_2| + BND3 |in_3| + BND4 (both nets;
+// stored in the spare floats of net 0's b3 block, whose 48 outputs leave 16 free)
+constexpr int SP_BND = SP_B3 + 56;
 
 // shared memory behind the image
 constexpr int OFF_Z = IMAGE_BYTES;                              // float [2 groups][36][128]: tz, A, B per z-row
@@ -94,6 +103,9 @@ constexpr int OFF_BAR = OFF_REF + NGROUPS * REF_SLOTS * 8 * 4;  // 2 mbarriers +
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
+#ifndef DP_TC_V_DEFAULT
+#define DP_TC_V_DEFAULT 0   // production variant V (see above); DP_TC_V overrides it at run time
+#endif
 #ifndef DP_SPLIT
 #define DP_SPLIT 2   // 0: F2FP + two conversions back, 1: mantissa truncation (LOP3), 2: mixed-precision FHADD (default)
 #endif
@@ -236,8 +248,10 @@ __device__ __forceinline__ float4 error_state(const SampleState &st, const float
     return make_float4(st.x0 - r.x, st.x1 - r.y, __fadd_rn(__fsub_rn(st.x2, r.z), st.x4), st.x3 - r.w);
 }
 
-template <int TP, int KC, int TR, int SG>
-__device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const SampleState &st, const float *ref, float (&acc)[4]) {
+template <int TP, int KC, int TR, int SG, int V>
+__device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const SampleState &st, const float *ref, float (&acc)[4],
+                                      const bool fast1) {
+    constexpr bool L1S = (V & 1) != 0, SH2 = (V & 2) != 0;
     const int N3 = NET == 0 ? N3A : N3B;
     const float *sp = c.small + NET * SMALL_NET_FLOATS;
     const uint64_t w2h = make_bdesc(c.sbase + (NET == 0 ? OFF_W2A_HI : OFF_W2B_HI), B_LBO, B_SBO);
@@ -274,7 +288,20 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                     y[e] = __ffma2_rn(make_float2(wc.x, wc.y), iz, y[e]);
                 }
                 float2 t[2];
-                tanh4(y[0], y[1], t[0], t[1]);
+                if (L1S) {
+                    // operand r = (1 + h1) / 2.  fast1 (warp-uniform): every |y| of this step is below the bound under
+                    // which the shared reciprocal needs neither |y| nor the sign copy
+                    if (fast1) {
+                        if (SH2) sigm4_pairs(y[0], y[1], t[0], t[1]);
+                        else sigm4_bounded(y[0], y[1], t[0], t[1]);
+                    } else {
+                        tanh4(y[0], y[1], t[0], t[1]);
+                        const float2 half2v = make_float2(0.5f, 0.5f);
+                        t[0] = __ffma2_rn(t[0], half2v, half2v);
+                        t[1] = __ffma2_rn(t[1], half2v, half2v);
+                    }
+                } else
+                    tanh4(y[0], y[1], t[0], t[1]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     SPLIT(t[e], av[pq + e], av[8 + pq + e]);
@@ -301,7 +328,10 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
 #pragma unroll
             for (int pq = 0; pq < 8; ++pq) {
                 const __half2 hi = bits_h2(hv[16 * j + pq]), lo = bits_h2(hv[16 * j + 8 + pq]);
-                g1[8 * j + pq] = h2_bits(__hfma2(__hmul2(m2, hi), lo, __hfma2(__hneg2(hi), hi, one2)));
+                if (L1S)  // (1 - h1^2) / 4 = r (1 - r) = hi (1 - hi) + lo (1 - 2 hi)
+                    g1[8 * j + pq] = h2_bits(__hfma2(lo, __hfma2(m2, hi, one2), __hfma2(__hneg2(hi), hi, hi)));
+                else
+                    g1[8 * j + pq] = h2_bits(__hfma2(__hmul2(m2, hi), lo, __hfma2(__hneg2(hi), hi, one2)));
             }
     }
     TRACE(1);
@@ -324,8 +354,9 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
     }
     uint32_t gs[32];
     {
-        const float2 *B2P = reinterpret_cast<const float2 *>(sp + SP_B2P);
-        const float2 cs = make_float2(C2SCALE, C2SCALE);
+        // fed with r, layer 2 sees W2 h1 = 2 W2 r - rowsum(W2): factor in the scale, row sums in the bias
+        const float2 *B2P = reinterpret_cast<const float2 *>(sp + (L1S ? SP_B2R : SP_B2P));
+        const float2 cs = make_float2(L1S ? 2.0f * C2SCALE : C2SCALE, L1S ? 2.0f * C2SCALE : C2SCALE);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int ch = 4 * h + i;
@@ -340,7 +371,8 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                 // SG: the layer-2 pre-activations are bounded by the weights (dp_tc_prepare), so no |y| / sign copy is
                 // needed, and layer 3 takes r = (1 + h2) / 2 as its operand (scale and bias adjusted in R4, gate = g2 / 4
                 // made up for in R56)
-                if (SG) sigm4_bounded(y0, y1, t[0], t[1]);
+                if (SG && SH2) sigm4_pairs(y0, y1, t[0], t[1]);
+                else if (SG) sigm4_bounded(y0, y1, t[0], t[1]);
                 else tanh4(y0, y1, t[0], t[1]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -387,7 +419,8 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         ld8(c.ra + 64 + 12 + 6 * h, v + 8);   // w2[1][6h .. 6h+5]
     }
     {
-        const uint32_t *c0h = reinterpret_cast<const uint32_t *>(sp + SP_C0H), *c1h = reinterpret_cast<const uint32_t *>(sp + SP_C1H);
+        const uint32_t *c0h = reinterpret_cast<const uint32_t *>(sp + (L1S ? SP_C0H4 : SP_C0H)),
+                       *c1h = reinterpret_cast<const uint32_t *>(sp + (L1S ? SP_C1H4 : SP_C1H));
         uint32_t gb[2][8];
         ld8(c.ra + stash_col(4 * h), gb[0]);
         wait_ld();
@@ -574,7 +607,7 @@ __device__ __forceinline__ void sample_advance(const RolloutParams &p, SampleSta
     st.x3 = __fadd_rn(st.x3, __fmul_rn(u1, dt));
 }
 
-template <int TP, int KC, int BATCH, int TR, int SG>
+template <int TP, int KC, int BATCH, int TR, int SG, int V>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     // the warp index through redux.sync: the compiler then knows that everything derived from it (group, feature half,
@@ -762,11 +795,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
             // in shared memory where they need them (nothing but the state stays in registers across a chain)
             const float *ref = sRef + (i & (REF_SLOTS - 1)) * 8;
             float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            bool fast1 = false;
+            if (V & 1) {
+                // bound of every scaled layer-1 pre-activation of this sample and step (both nets); the sign-free sigmoid
+                // with a shared reciprocal is exact while 2^-y of the sharing arguments multiply to a normal number
+                const float *bnd = c.small + SP_BND;
+                const float inz = st.x2 - __fadd_rn(__fsub_rn(st.x2, ref[2]), st.x4);
+                const float B = fmaf(bnd[0], fabsf(st.x2), fmaf(bnd[1], fabsf(st.x3), fmaf(bnd[2], fabsf(inz), fmaf(bnd[3], fabsf(ref[3]), bnd[4]))));
+                fast1 = __all_sync(0xffffffffu, B < ((V & 2) ? 62.5f : 31.0f));
+            }
 #pragma unroll 1
             for (int net = 0; net < 2; ++net) {  // net a, then net b; the two TMEM regions swap roles
                 const uint32_t A = net == 0 ? R0 : R1, Dd = net == 0 ? R1 : R0;
                 c.RA = A; c.RD = Dd; c.ra = A + lane_off; c.rd = Dd + lane_off;
-                chain<TP, KC, TR, SG>(c, ph, net, st, ref, acc);
+                chain<TP, KC, TR, SG, V>(c, ph, net, st, ref, acc, fast1);
             }
             // exchange the partial head sums of the two feature halves (fixed order: both threads get identical totals)
             float *mine = sPart + h * 4 * TILE + c.s;
@@ -806,7 +848,7 @@ int dp_tc_prepare(dp_controller *c, const float *blob) {
     const int off_w2h[2] = {OFF_W2A_HI, OFF_W2B_HI}, off_w2l[2] = {OFF_W2A_LO, OFF_W2B_LO};
     const int off_w3h[2] = {OFF_W3A_HI, OFF_W3B_HI}, off_w3l[2] = {OFF_W3A_LO, OFF_W3B_LO};
     const double k = 2.8853900817779268;  // 2 log2(e)
-    double l2_bound = 0.0;
+    double l2_bound = 0.0, l1_bound[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     for (int m = 0; m < 2; ++m) {
         float *sp = reinterpret_cast<float *>(img.data() + OFF_SMALL) + m * SMALL_NET_FLOATS;
         const float *W1 = p; p += 512;
@@ -820,7 +862,14 @@ int dp_tc_prepare(dp_controller *c, const float *blob) {
             __half2 c1 = __floats2half2_rn(W1[4 * (2 * j) + 1], W1[4 * (2 * j + 1) + 1]);
             memcpy(sp + SP_C0H + j, &c0, 4);
             memcpy(sp + SP_C1H + j, &c1, 4);
+            __half2 c04 = __floats2half2_rn(4.0f * W1[4 * (2 * j)], 4.0f * W1[4 * (2 * j + 1)]);
+            __half2 c14 = __floats2half2_rn(4.0f * W1[4 * (2 * j) + 1], 4.0f * W1[4 * (2 * j + 1) + 1]);
+            memcpy(sp + SP_C0H4 + j, &c04, 4);
+            memcpy(sp + SP_C1H4 + j, &c14, 4);
         }
+        for (int cc = 0; cc < 4; ++cc)
+            for (int j = 0; j < 128; ++j) l1_bound[cc] = fmax(l1_bound[cc], k * fabs((double)W1[4 * j + cc]));
+        for (int j = 0; j < 128; ++j) l1_bound[4] = fmax(l1_bound[4], k * fabs((double)b1[j]));
         for (int j = 0; j < 128; ++j) sp[SP_B1P + j] = (float)(k * b1[j]);
         build_split_image(p, 128, 128, WSCALE, reinterpret_cast<__half *>(img.data() + off_w2h[m]),
                           reinterpret_cast<__half *>(img.data() + off_w2l[m]));
@@ -830,6 +879,8 @@ int dp_tc_prepare(dp_controller *c, const float *blob) {
             for (int j = 0; j < 128; ++j) l1 += fabs((double)p[128 * r + j]);
             if (k * l1 > l2_bound) l2_bound = k * l1;
         }
+        for (int j = 0; j < 128; ++j)
+            sp[SP_B2R + j] = (float)(k * ((double)p[128 * 128 + j] - split_image_rowsum(p, j, WSCALE) / (double)WSCALE));
         p += 128 * 128;
         for (int j = 0; j < 128; ++j) sp[SP_B2P + j] = (float)(k * p[j]);
         p += 128;
@@ -850,6 +901,10 @@ int dp_tc_prepare(dp_controller *c, const float *blob) {
         }
         p += nouts[m] * 128 + nouts[m];
     }
+    {
+        float *sp0 = reinterpret_cast<float *>(img.data() + OFF_SMALL);
+        for (int i = 0; i < 5; ++i) sp0[SP_BND + i] = (float)(l1_bound[i] * (1.0 + 1e-6));
+    }
     void *d = nullptr;
     DP_CUDA(cudaMalloc(&d, IMAGE_BYTES));
     DP_CUDA(cudaMemcpy(d, img.data(), IMAGE_BYTES, cudaMemcpyHostToDevice));
@@ -858,6 +913,7 @@ int dp_tc_prepare(dp_controller *c, const float *blob) {
     // below 2^126 (the reciprocal must stay a normal number), i.e. every |y| below 31.5 (plus the rounding of the split
     // operands, far below the margin kept here)
     c->tc_l2_bounded = l2_bound < 31.4;
+    c->tc_l2_bound = (float)l2_bound;
     return 0;
 }
 
@@ -871,14 +927,22 @@ int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStr
     static bool attr_set[64] = {};
     static int variant = -1;  // tuning / A-B knob: DP_TC_VARIANT = 100 * K-chunking (0 off, 1 on) + 10 * tangent products
     typedef void (*kern_t)(RolloutParams);
-    static const kern_t kerns[4] = {rollout_tc_kernel<1, 0, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0, 0>,
-                                    rollout_tc_kernel<2, 0, 0, 0, 0>, rollout_tc_kernel<2, 1, 0, 0, 0>};
-    // the default variant and the batched one also exist with the sign-free layer-2 tanh (tanh4_bounded); the host picks
-    // them when the weights bound the layer-2 pre-activations (c->tc_l2_bounded, see dp_tc_prepare)
-    static const kern_t kern_bounded = rollout_tc_kernel<1, 1, 0, 0, 1>;
-    static const kern_t kern_batch[2] = {rollout_tc_kernel<1, 1, 1, 0, 0>, rollout_tc_kernel<1, 1, 1, 0, 1>};  // dp_rollout_batch
-    static const kern_t kern_trace = rollout_tc_kernel<1, 1, 0, 1, 0>;  // with the in-kernel timeline (DP_TC_TRACE)
+    static const kern_t kerns[4] = {rollout_tc_kernel<1, 0, 0, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0, 0, 0>,
+                                    rollout_tc_kernel<2, 0, 0, 0, 0, 0>, rollout_tc_kernel<2, 1, 0, 0, 0, 0>};
+    // The production kernels [batch][SG][V]: TP = 1, K-chunked issue.  SG: sign-free layer-2 sigmoid, picked by the host when
+    // the weights bound the layer-2 pre-activations (dp_tc_prepare); V: see the top of this file (DP_TC_V, default below).
+    static const kern_t prod[2][2][4] = {
+        {{rollout_tc_kernel<1, 1, 0, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0, 0, 1>, rollout_tc_kernel<1, 1, 0, 0, 0, 2>,
+          rollout_tc_kernel<1, 1, 0, 0, 0, 3>},
+         {rollout_tc_kernel<1, 1, 0, 0, 1, 0>, rollout_tc_kernel<1, 1, 0, 0, 1, 1>, rollout_tc_kernel<1, 1, 0, 0, 1, 2>,
+          rollout_tc_kernel<1, 1, 0, 0, 1, 3>}},
+        {{rollout_tc_kernel<1, 1, 1, 0, 0, 0>, rollout_tc_kernel<1, 1, 1, 0, 0, 1>, rollout_tc_kernel<1, 1, 1, 0, 0, 2>,
+          rollout_tc_kernel<1, 1, 1, 0, 0, 3>},
+         {rollout_tc_kernel<1, 1, 1, 0, 1, 0>, rollout_tc_kernel<1, 1, 1, 0, 1, 1>, rollout_tc_kernel<1, 1, 1, 0, 1, 2>,
+          rollout_tc_kernel<1, 1, 1, 0, 1, 3>}}};
+    static const kern_t kern_trace = rollout_tc_kernel<1, 1, 0, 1, 0, 0>;  // with the in-kernel timeline (DP_TC_TRACE)
     static int bounded_ok = -1;  // DP_TC_BOUNDED=0 forces the general tanh (A/B and test knob)
+    static int vsel = DP_TC_V_DEFAULT;
     if (variant < 0) {
         const char *e = getenv("DP_TC_VARIANT");
         const int v = e ? atoi(e) : 110;
@@ -886,20 +950,24 @@ int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStr
         variant = 2 * tp + kc;
         const char *b = getenv("DP_TC_BOUNDED");
         bounded_ok = (b && atoi(b) == 0) ? 0 : 1;
+        const char *vs = getenv("DP_TC_V");
+        if (vs) vsel = atoi(vs) & 3;
     }
     if (!attr_set[c->device & 63]) {
         for (int k = 0; k < 4; ++k)
             DP_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        DP_CUDA(cudaFuncSetAttribute(kern_bounded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        DP_CUDA(cudaFuncSetAttribute(kern_batch[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        DP_CUDA(cudaFuncSetAttribute(kern_batch[1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        for (int b = 0; b < 2; ++b)
+            for (int g = 0; g < 2; ++g)
+                for (int k = 0; k < 4; ++k)
+                    DP_CUDA(cudaFuncSetAttribute(prod[b][g][k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         DP_CUDA(cudaFuncSetAttribute(kern_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_set[c->device & 63] = true;
     }
     const bool batch = p.R > 1 || p.T_ref != nullptr;
     const char *trace_path = getenv("DP_TC_TRACE");  // diagnostic: dump an in-kernel clock64 timeline of CTA 0
-    const bool bounded = bounded_ok && c->tc_l2_bounded;
-    const kern_t kern = batch ? kern_batch[bounded] : (trace_path ? kern_trace : (bounded && variant == 1 ? kern_bounded : kerns[variant]));
+    // the shared reciprocal of the sign-free layer-2 sigmoid needs |y| < 31.4 (four arguments) or < 62.8 (pairs, V & 2)
+    const bool bounded = bounded_ok && c->tc_l2_bound < ((vsel & 2) ? 62.8f : 31.4f);
+    const kern_t kern = (!batch && trace_path) ? kern_trace : ((!batch && variant != 1) ? kerns[variant] : prod[batch][bounded][vsel]);
     RolloutParams q = p;
     q.tc = c->d_tc;
     const long long num_tiles = (p.R > 1 || p.T_ref) ? p.R * ((p.n_per_ref + TILE - 1) / TILE) : (p.N + TILE - 1) / TILE;

@@ -24,7 +24,7 @@ constexpr int OFF_W3A_LO = OFF_W3A_HI + W3A_BYTES;
 constexpr int OFF_W3B_HI = OFF_W3A_LO + W3A_BYTES;
 constexpr int OFF_W3B_LO = OFF_W3B_HI + W3B_BYTES;
 constexpr int OFF_SMALL = OFF_W3B_LO + W3B_BYTES;  // per-net fp32 block (layout owned by each kernel), 1024 floats per net
-constexpr int SMALL_NET_FLOATS = 1024;
+constexpr int SMALL_NET_FLOATS = 1280;
 constexpr int IMAGE_BYTES = OFF_SMALL + 2 * SMALL_NET_FLOATS * 4;
 static_assert(IMAGE_BYTES % 16 == 0, "image copied with 16-byte vectors");
 
@@ -195,6 +195,18 @@ __device__ __forceinline__ void sigm4_bounded(const float2 yA, const float2 yB, 
     const float2 q = make_float2(R * p.y, R * p.x);
     rA = __fmul2_rn(q, aB);
     rB = __fmul2_rn(q, aA);
+}
+// The same with TWO reciprocals: the pairs (0,2) and (1,3) share one each (packed products only: 11 instructions for four
+// arguments instead of 13, 1.5 MUFU per argument instead of 1.25).  The product of two denominators stays a normal number with a
+// normal reciprocal while every y > -63 (caller's contract).
+__device__ __forceinline__ void sigm4_pairs(const float2 yA, const float2 yB, float2 &rA, float2 &rB) {
+    const float2 one = make_float2(1.0f, 1.0f);
+    const float2 aA = __fadd2_rn(make_float2(ex2_approx(-yA.x), ex2_approx(-yA.y)), one);
+    const float2 aB = __fadd2_rn(make_float2(ex2_approx(-yB.x), ex2_approx(-yB.y)), one);
+    const float2 p = __fmul2_rn(aA, aB);                                     // (a0 a2, a1 a3)
+    const float2 R = make_float2(rcp_approx(p.x), rcp_approx(p.y));
+    rA = __fmul2_rn(R, aB);                                                  // (1/a0, 1/a1)
+    rB = __fmul2_rn(R, aA);                                                  // (1/a2, 1/a3)
 }
 __device__ __forceinline__ uint32_t h2_bits(const __half2 h) { return *reinterpret_cast<const uint32_t *>(&h); }
 __device__ __forceinline__ __half2 bits_h2(const uint32_t u) { return *reinterpret_cast<const __half2 *>(&u); }

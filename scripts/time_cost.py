@@ -36,8 +36,13 @@ mass = torch.zeros((Ts, cells), dtype=torch.int64, device=dev); count = torch.ze
 def bin2d():
     _lib.check(L.dp_bin2d(ctypes.byref(spec), _lib.ptr(x), _lib.ptr(y), 1, N, _lib.ptr(rho), 1, N, N, Ts, _lib.ptr(mass),
                           _lib.ptr(count), sp), "bin2d")
+dot = torch.empty(Ts, dtype=torch.float64, device=dev)
+def bin2d_occ():
+    _lib.check(L.dp_bin2d_occ(ctypes.byref(spec), denv.handle, _lib.ptr(x), _lib.ptr(y), 1, N, _lib.ptr(rho), 1, N, N, Ts,
+                              _lib.ptr(mass), _lib.ptr(count), _lib.ptr(dot), sp), "bin2d_occ")
 peak = 6554.9
-for name, fn, bytes_per in (("cost fwd", fwd, 12), ("cost fwd+bwd", fwdbwd, 24), ("bin2d", bin2d, 12)):
+print("knobs: DP_BIN_THREADS=%s DP_BIN_AGG=%s" % (os.environ.get("DP_BIN_THREADS", "default"), os.environ.get("DP_BIN_AGG", "default")))
+for name, fn, bytes_per in (("cost fwd", fwd, 12), ("cost fwd+bwd", fwdbwd, 24), ("bin2d", bin2d, 12), ("bin2d_occ", bin2d_occ, 12)):
     for _ in range(3): fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); reps = 10

@@ -68,11 +68,15 @@ def test_rollout_vs_reference_golden(car, impl, name):
     assert np.abs(margin - g["clip_margin"]).max() < 1e-3
 
 
-@pytest.mark.parametrize("env", [{"DP_TC_BOUNDED": "0"}, {"DP_TC_VARIANT": "120"}, {"DP_TC_VARIANT": "20"}])
+@pytest.mark.parametrize("env", [{"DP_TC_BOUNDED": "0"}, {"DP_TC_VARIANT": "120"}, {"DP_TC_VARIANT": "20"},
+                                 {"DP_TC_V": "0"}, {"DP_TC_V": "1"}, {"DP_TC_V": "2"}, {"DP_TC_V": "3"},
+                                 {"DP_TC_V": "3", "DP_TC_BOUNDED": "0"}])
 def test_rollout_kernel_variants_vs_reference_golden(env):
     """The variants the host does not pick by default -- the general tanh (what a controller whose layer-2 weights do not
-    bound the pre-activations gets), two tangent products with and without K-chunked MMA issue -- against the same golden
-    vectors; one fresh process each because the knobs are read once per process."""
+    bound the pre-activations gets), two tangent products with and without K-chunked MMA issue, and every production variant
+    V (layer 1 handing r = (1 + h1) / 2 to layer 2 with the per-step bound check -- with the four-argument reciprocal, V = 1,
+    these states exceed the bound regularly, so both the sign-free and the general branch run -- and the pair reciprocal) --
+    against the same golden vectors; one fresh process each because the knobs are read once per process."""
     import os
     import subprocess
     import sys
