@@ -384,17 +384,44 @@ def get_cost_coll(x_traj, rho_traj, denv, get_max=False):
     return _CollisionCost.apply(x_traj, rho_traj, denv, bool(get_max))
 
 
+class _CollisionCostInit(torch.autograd.Function):
+    """cost[n] = sum_i p(cell) * |des(cell) - x[n,:2,i]|^2 per trajectory (MotionPlannerGrad.py:309-336), grid indices
+    constant (no_grad, :321-324): d cost[n] / d x[n,:2,i] = -2 p (des - x), evaluated by the same kernel pass."""
+
+    @staticmethod
+    def forward(ctx, x_traj, denv):
+        dev = denv.device
+        x = _as_dev_2d(x_traj[:, 0, :], dev)
+        y = _as_dev_2d(x_traj[:, 1, :], dev)
+        if x.stride() != y.stride():
+            x, y = x.contiguous(), y.contiguous()
+        need = x_traj.requires_grad
+        _, samples, gx, gy, _ = _cost_call(denv, x, y, None, False, need, True)
+        if need:
+            ctx.save_for_backward(gx, gy)
+        ctx.meta = (x_traj.shape, x_traj.device, need)
+        return samples.to(dtype=torch.float32, device=x_traj.device)
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, xdev, need = ctx.meta
+        if not need:
+            return None, None
+        gx, gy = ctx.saved_tensors
+        gd = g.to(device=gx.device, dtype=torch.float32).reshape(-1, 1)
+        gxt = torch.zeros(shape, dtype=torch.float32, device=xdev)
+        gxt[:, 0, :] = (gx * gd).to(xdev)
+        gxt[:, 1, :] = (gy * gd).to(xdev)
+        return gxt, None
+
+
 def get_cost_coll_initialize(x_traj, denv):
     """MotionPlannerGrad.get_cost_coll_initialize (motion_planning/MotionPlannerGrad.py:309-336): per-trajectory cost
-    (num_traj,), no density weights.  Forward only here (the reference differentiates it w.r.t. the up parameters
-    through up2ref_traj; that autograd graph is SURVEY section 8f item 1, not yet kernel-backed)."""
-    dev = denv.device
-    x = _as_dev_2d(x_traj[:, 0, :], dev)
-    y = _as_dev_2d(x_traj[:, 1, :], dev)
-    if x.stride() != y.stride():
-        x, y = x.contiguous(), y.contiguous()
-    _, samples, _, _, _ = _cost_call(denv, x, y, None, False, False, True)
-    return samples.to(dtype=torch.float32, device=x_traj.device)
+    (num_traj,), no density weights; differentiable w.r.t. x_traj[:, :2, :] (the initialisation phase of the planner
+    differentiates it w.r.t. the up parameters through up2ref_traj, :56-96,138)."""
+    if x_traj.shape[0] == 0:
+        return torch.zeros(0, dtype=torch.float32, device=x_traj.device)
+    return _CollisionCostInit.apply(x_traj, denv)
 
 
 # ---- goal / bounds cost terms of MotionPlanner.get_cost (SURVEY section 8f row 3) --------------------------------------

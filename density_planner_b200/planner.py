@@ -152,13 +152,8 @@ def attach(planner, device=None):
     cc = CollisionCost.from_ego(ego, device)
     planner.get_cost_coll = cc.get_cost_coll
     if hasattr(planner, "get_cost_coll_initialize"):
-        init_ref = planner.get_cost_coll_initialize
-
-        def _init(x_traj):
-            # the initialisation phase differentiates through this cost w.r.t. up; keep the reference there
-            return init_ref(x_traj) if x_traj.requires_grad else cc.get_cost_coll_initialize(x_traj)
-
-        planner.get_cost_coll_initialize = _init
+        # forward + analytic backward on the kernel: the whole initialisation phase (MotionPlannerGrad.py:56-96) runs on it
+        planner.get_cost_coll_initialize = cc.get_cost_coll_initialize
     system = Car(ego.args, device=device)
     nn = None
     model = getattr(ego, "model", None)

@@ -369,9 +369,50 @@ def gen_data(car, args):
     save("compute_data.npz", **out)
 
 
+def gen_cost_init_grad(car, args):
+    """MotionPlannerGrad.get_cost_coll_initialize (MotionPlannerGrad.py:309-336) differentiated w.r.t. the trajectories, as
+    the planner's initialisation phase does (:138): per-trajectory costs and the gradient of a weighted sum, environments 0, 1,
+    inputs = the first 100 LE trajectories of env_seed{0,1}.npz; and the goal term with a density LONGER than the states
+    (MotionPlanner.py:139-141 uses rho_traj[:, 0, -1]: the LE branch returns 101 states and 1001 densities)."""
+    rh.install()
+    with rh.ref_cwd():
+        from motion_planning.example_objects import create_mp_task
+        from motion_planning.MotionPlannerGrad import MotionPlannerGrad
+    os.makedirs("/tmp/dp_log", exist_ok=True)
+    out = {}
+    for seed in (0, 1):
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        with rh.ref_cwd():
+            ego = create_mp_task(args, seed)
+            planner = MotionPlannerGrad(ego, path_log="/tmp/dp_log/")
+        e = np.load(os.path.join(HERE, "env_seed%d.npz" % seed))
+        x5 = torch.zeros(100, 5, 101)
+        x5[:, :2, :] = torch.from_numpy(e["le_x"][:100])
+        x5.requires_grad_(True)
+        c = planner.get_cost_coll_initialize(x5)
+        w = torch.linspace(0.5, 1.5, 100)
+        (w * c).sum().backward()
+        out["s%d_cost" % seed] = c.detach().numpy()
+        out["s%d_gx" % seed] = x5.grad[:, :2, :].numpy()
+        # goal term, density with 1001 time points against states with 101
+        x_all = torch.zeros(500, 5, 101)
+        x_all[:, :2, :] = torch.from_numpy(e["le_x"])
+        x_all.requires_grad_(True)
+        rho = torch.from_numpy(e["le_rho"]).unsqueeze(1).clone().requires_grad_(True)
+        cg, close = planner.get_cost_goal(x_all, rho, evaluate=True)
+        cg.backward()
+        out["s%d_goal" % seed] = cg.detach().numpy()
+        out["s%d_goal_gx_last" % seed] = x_all.grad[:, :2, -1].numpy()
+        out["s%d_goal_grho_last" % seed] = rho.grad[:, 0, -1].numpy()
+        out["s%d_goal_grho_at100" % seed] = rho.grad[:, 0, 100].numpy()
+        out["s%d_xrefN" % seed] = ego.xrefN[0, :, 0].numpy()
+    save("cost_init_grad.npz", **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="weights,rollout,step,grid,env,data,planner,nn")
+    ap.add_argument("--only", default="weights,rollout,step,grid,env,data,planner,nn,initgrad")
     ap.add_argument("--env-seeds", default="0,1,2,3,4,5,6,7,8,9")
     a = ap.parse_args()
     which = a.only.split(",")
@@ -393,6 +434,8 @@ def main():
         gen_planner_terms(car, args)
     if "nn" in which:
         gen_density_nn(car, args)
+    if "initgrad" in which:
+        gen_cost_init_grad(car, args)
     print("done in %.1f s" % (time.time() - t0))
 
 

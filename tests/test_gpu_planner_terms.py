@@ -131,3 +131,47 @@ def test_density_nn_on_gpu_matches_reference_golden(dp, args):
     assert np.abs(rho_traj.detach()[:, 0, :].numpy() - g["rho_traj"]).max() < 1e-4 * g["rho_traj"].max()
     (torch.from_numpy(g["w"]) * x_traj).sum().backward()
     assert up.grad is not None and bool(torch.isfinite(up.grad).all())
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_cost_coll_initialize_gradient_and_goal_with_long_density(dp, oracle, args, seed):
+    """(1) get_cost_coll_initialize forward + analytic backward against the reference's autograd (golden minted from
+    MotionPlannerGrad.get_cost_coll_initialize, :309-336, on the first 100 LE trajectories): the planner's initialisation
+    phase differentiates this cost.  (2) the goal term when rho_traj has more time points than x_traj (the LE branch: 101
+    states, 1001 densities): the reference weights the last state with rho_traj[:, 0, -1] (MotionPlanner.py:139-141)."""
+    g = golden("cost_init_grad.npz")
+    e = golden("env_seed%d.npz" % seed)
+    gx, gy = oracle.env_gradient(e["grid"])
+    cc = dp.CollisionCost(torch.from_numpy(e["grid"]), torch.from_numpy(gx), torch.from_numpy(gy), args)
+    x5 = torch.zeros(100, 5, 101)
+    x5[:, :2, :] = torch.from_numpy(e["le_x"][:100])
+    x5.requires_grad_(True)
+    c = cc.get_cost_coll_initialize(x5)
+    assert c.shape == (100,) and c.requires_grad
+    ref_c = g["s%d_cost" % seed]
+    assert np.abs(c.detach().numpy() - ref_c).max() <= 1e-4 * np.abs(ref_c).max()
+    w = torch.linspace(0.5, 1.5, 100)
+    (w * c).sum().backward()
+    ref_g = g["s%d_gx" % seed]
+    assert float(x5.grad[:, 2:, :].abs().max()) == 0.0
+    assert np.abs(x5.grad[:, :2, :].numpy() - ref_g).max() <= 2e-6 * np.abs(ref_g).max()
+    assert ((x5.grad[:, :2, :].numpy() != 0) == (ref_g != 0)).all()
+    # CUDA inputs in the kernel's own layout take the same path
+    xc = x5.detach().cuda().requires_grad_(True)
+    cc.get_cost_coll_initialize(xc).sum().backward()
+    assert xc.grad.is_cuda and bool(torch.isfinite(xc.grad).all())
+    # no gradient requested: forward only
+    assert not cc.get_cost_coll_initialize(x5.detach()).requires_grad
+    # (2) goal term, density longer than the states
+    x_all = torch.zeros(500, 5, 101)
+    x_all[:, :2, :] = torch.from_numpy(e["le_x"])
+    x_all.requires_grad_(True)
+    rho = torch.from_numpy(e["le_rho"]).unsqueeze(1).clone().requires_grad_(True)
+    xrefN = torch.from_numpy(g["s%d_xrefN" % seed]).reshape(1, 5, 1)
+    cg, close = dp.get_cost_goal(x_all, rho, xrefN, args, evaluate=True)
+    ref_goal = float(g["s%d_goal" % seed])
+    assert abs(float(cg) - ref_goal) <= 1e-4 * abs(ref_goal)
+    cg.backward()
+    assert np.abs(x_all.grad[:, :2, -1].numpy() - g["s%d_goal_gx_last" % seed]).max() <= 1e-5 * np.abs(g["s%d_goal_gx_last" % seed]).max()
+    assert np.abs(rho.grad[:, 0, -1].numpy() - g["s%d_goal_grho_last" % seed]).max() <= 1e-5 * np.abs(g["s%d_goal_grho_last" % seed]).max()
+    assert float(rho.grad[:, 0, 100].abs().max()) == 0.0 and float(x_all.grad[:, :, :-1].abs().max()) == 0.0
