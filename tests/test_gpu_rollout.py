@@ -239,7 +239,8 @@ def _check_rawdata_against_golden(car, args, res, g):
         up, uref, xref = car.get_valid_ref(args)
         xe0 = car.sample_xe0(20)
         torch.randint(0, xref[:, :, ::k].shape[2], (10,))          # the time-index draw consumes the RNG
-        assert (xe0[:, :, 0].numpy() == g["r%d_xe0" % i]).all()
+        # (the stored 'xe0' is the rollout's slice 0, i.e. (xe0 + xref0) - xref0: equal to the drawn xe0 up to one rounding)
+        assert np.abs(xe0[:, :, 0].numpy() - g["r%d_xe0" % i]).max() < 1e-5
         xe, rho, margin = car.compute_density(xe0.cuda(), xref, uref, args.dt_sim, log_density=True, return_margin=True)
         idx = np.rint(r["t"].numpy() / (args.dt_sim * k)).astype(int)
         assert bool((xe.cpu()[:, :, ::k][:, :, idx] == r["xe_traj"]).all())    # compute_data returned this very rollout
