@@ -2,7 +2,8 @@
 """Benchmark of the density_planner hot path on B200 (contract: see the task statement / DESIGN.md section 6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework's arm
-    python bench.py --impl reference [--gpus N] ...                 # CPU arm: the oracle port on the host cores
+    python bench.py --impl reference [--gpus N] ...                 # CPU arm: the reference's own compute_density on the host
+                                                                    # cores (baseline/_ref; the oracle port if it is absent)
 
 One "step" = one pass of the hot path over one batch of synthetic input on every rank, through the device-resident
 pipeline (density_planner_b200/pipeline.py, dp_pipeline_*):
@@ -170,6 +171,43 @@ def cpu_oracle_rate(target_seconds=12.0):
                       "analytic divergence, OpenMP over samples), %.1f s" % (n, STEPS, dt)}, n, dt
 
 
+def cpu_reference_rate(target_seconds=12.0):
+    """Times the reference's OWN compute_density (systems/ControlAffineSystem.py:409-463: per step three forward passes and
+    two autograd passes over the whole sample batch, PyTorch on the host cores) on a bounded sample of the workload.  The
+    unmodified reference tree travels to the GPU box as the git-ignored copy baseline/_ref/ (baseline/make_ref.sh); returns
+    None when it is absent."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "systems")):
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import ref_harness as rh
+    rh.REF_ROOT = ref_root
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    torch.set_num_threads(cores)  # torchrun exports OMP_NUM_THREADS=1 by default
+    car, a = rh.make_car()
+    torch.manual_seed(0)
+    with rh.ref_cwd():
+        while True:  # get_valid_trajectories' rejection sampling of the reference (:465-475)
+            uref, _ = car.sample_uref_traj(a)
+            xref = car.compute_xref_traj(car.sample_xref0(), uref, a)
+            xref, uref = car.cut_xref_traj(xref, uref)
+            if xref.shape[2] > 0.99 * a.N_sim:
+                break
+        n = 20000  # the reference's per-step cost is flat below ~1e4 samples (Python / autograd overhead), linear above
+        xe0 = car.sample_xe0(n)
+        t0 = time.perf_counter()
+        car.compute_density(xe0, xref[:, :, :5], uref[:, :, :4], a.dt_sim, cutting=True, log_density=True)
+        per_step = (time.perf_counter() - t0) / 4
+        steps = int(min(max(target_seconds / per_step, 4), STEPS))
+        t0 = time.perf_counter()
+        car.compute_density(xe0, xref[:, :, :steps + 1], uref[:, :, :steps], a.dt_sim, cutting=True, log_density=True)
+        dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "%d samples x %d steps of the same rollout through the UNMODIFIED reference's Car.compute_density "
+                      "(PyTorch CPU, autograd divergence, %d threads), %.1f s" % (n, steps, cores, dt)}, n * steps, dt
+
+
 def run_reference_arm(opts):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -177,16 +215,26 @@ def run_reference_arm(opts):
     t_all = time.perf_counter()
     base = None
     times = []
+    budget = 6.0 if opts.steps > 1 else 12.0
+    use_ref = cpu_reference_rate(target_seconds=2.0) is not None  # the reference itself when its tree is on the box
     for i in range(opts.warmup + opts.steps):
-        base, n, dt = cpu_oracle_rate(target_seconds=6.0 if opts.steps > 1 else 12.0)
+        if use_ref:
+            base, units, dt = cpu_reference_rate(target_seconds=budget)
+        else:
+            base, n, dt = cpu_oracle_rate(target_seconds=budget)
+            units = n * STEPS
         if i >= opts.warmup:
-            times.append((n, dt))
+            times.append((units, dt))
         if time.perf_counter() - t_all > 240:
             break
-    tot_n = sum(n for n, _ in times)
+    if not times:
+        times.append((units, dt))
+    tot_u = sum(u for u, _ in times)
     tot_t = sum(dt for _, dt in times)
-    value = tot_n * STEPS / tot_t
+    value = tot_u / tot_t
     base["value"] = value
+    if use_ref:  # the C restatement beside it (analytic divergence, OpenMP): what the reference could do on the same cores
+        base["port"] = cpu_oracle_rate(target_seconds=6.0)[0]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": opts.gpus,
             "steps": len(times), "warmup": opts.warmup, "ms_per_step": 1e3 * tot_t / max(len(times), 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -549,7 +597,13 @@ def main():
             "collision_cost_evals_per_s": cfg3["cost_fwd"]["evals_per_s"] if cfg3 else None,
             "collision_cost_config3": cfg3, "rawdata_config1": cfg1, "checks": checks}
     if not opts.no_cpu_baseline and world == 1:
-        base, _, _ = cpu_oracle_rate()
+        ref = cpu_reference_rate()
+        port, _, _ = cpu_oracle_rate()
+        if ref is not None:  # the reference's own PyTorch path; the C port beside it
+            base = ref[0]
+            base["port"] = port
+        else:
+            base = port
         line["cpu_baseline"] = base
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())

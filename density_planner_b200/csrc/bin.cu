@@ -289,6 +289,181 @@ __global__ void __launch_bounds__(NT, 2) bin2d_kernel(BinArgs a) {
     }
 }
 
+// ---- lean kernel (mode 0, contiguous 16-byte aligned rows, mass and count both wanted): the default path ---------------------
+// ncu of the general kernel above at the config-3 size (profiles/r02_bin2d_before_ncu.txt) showed it ISSUE bound (issue slots
+// 91 % active, 101 thread instructions per sample, shared-atomic wavefronts only 21 % of peak, DRAM 39 %), not atomic bound:
+// the warp collectives that keep lanes converged for match.any / redux, the run-time knobs and the 64-bit index arithmetic were
+// most of the instructions.  This kernel has no warp collective at all in the sample loop:
+//   * cell index: the reference's fp32 op sequence up to q + 0.001, then clamp IN FLOAT to [0, G] and round with the magic-number
+//     add (t + 1.5 * 2^23 has rn(t) in its low mantissa bits, ties to even like cvt.rni / torch.round).  Rounding is monotone
+//     and fixes the integers 0 and G, so rn(clamp(t)) = clamp(rn(t)): same cells as dp_cell + integer clamp, NaN -> 0 as before;
+//     two F2I (XU pipe) and the integer clamps become FMNMX + FADD, and the window offset absorbs the magic constant.
+//   * a sample outside the block's window goes straight to global atomics from its own lane (no match.any): such samples are
+//     rare for the clouds this path sees, and a diffuse cloud is bound by the global atomics either way.
+//   * no aggregation before the shared atomics: measured 15x slower with match.any (gpurun r2: 5.96 ms vs 0.41 ms), and even a
+//     cloud contracted to a few cells costs ~6 wavefronts per atomic, i.e. about the DRAM time of the pass.
+// Results are integer sums, so they equal the general kernel's bit for bit (tests: knob A/B fingerprints, permutation / shard
+// invariance).
+__device__ __forceinline__ int lean_cell_biased(float p, float lo, float rng, float r_rng, float gm1, float cmax) {
+    const float q = __fmul_rn(dp_div_fast(__fsub_rn(p, lo), rng, r_rng), gm1);
+    const float t = fminf(fmaxf(__fadd_rn(q, 0.001f), 0.0f), cmax);
+    return __float_as_int(__fadd_rn(t, 12582912.0f));  // 0x4B400000 + rn(t)
+}
+constexpr int LEAN_MAGIC = 0x4B400000;
+
+template <bool FUSED, bool OCC, bool HASW, int NT>
+__global__ void __launch_bounds__(NT, 2) bin2d_lean_kernel(BinArgs a) {
+    constexpr int VW = FUSED ? 2 : 4;  // samples per thread and iteration (the fused pass carries more state per sample)
+    extern __shared__ __align__(16) unsigned char bsm[];
+    unsigned *slo = reinterpret_cast<unsigned *>(bsm);
+    unsigned *shi = reinterpret_cast<unsigned *>(bsm + WIN * WIN * 4);
+    int *scount = reinterpret_cast<int *>(bsm + WIN * WIN * 8);
+    int *sorg = reinterpret_cast<int *>(bsm + WIN * WIN * 12);
+    __shared__ double shd[NT / 32];
+    __shared__ long long shq[NT / 32];
+    const int t = blockIdx.y, tid = threadIdx.x;
+    const float4 *xp = reinterpret_cast<const float4 *>(a.x + (long long)t * a.sx_t);
+    const float4 *yp = reinterpret_cast<const float4 *>(a.y + (long long)t * a.sx_t);
+    const float4 *wp = HASW ? reinterpret_cast<const float4 *>(a.w + (long long)t * a.sw_t) : nullptr;
+    const float4 *rp = (FUSED && a.rho0) ? reinterpret_cast<const float4 *>(a.rho0) : nullptr;
+    const int cells = a.cx * a.cy;
+    unsigned long long *mass = reinterpret_cast<unsigned long long *>(a.mass + (long long)t * cells);
+    int *count = a.count + (long long)t * cells;
+    const float4 *tab = (FUSED || OCC) ? a.table + (size_t)t * a.egx * a.egy : nullptr;
+    const float mx = FUSED ? __ldg(a.lmax + t) : 0.0f;
+    const float cmx = (float)(a.cx - 1), cmy = (float)(a.cy - 1);
+    long long chunk = (a.N + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + 3) & ~3LL;
+    const long long n_lo = min((long long)blockIdx.x * chunk, a.N), n_hi = min(n_lo + chunk, a.N);
+    if (tid < 32) {  // window origin: mean cell of 32 probe samples spread over the chunk (any choice gives the same grids)
+        int sx = 0, sy = 0, sk = 0;
+        if (n_lo < n_hi) {
+            const long long n = n_lo + (n_hi - n_lo) * tid / 32;
+            const float *xs = reinterpret_cast<const float *>(xp), *ys = reinterpret_cast<const float *>(yp);
+            sx = lean_cell_biased(__ldg(xs + n), a.q.x_lo, a.q.x_rng, a.q.r_x_rng, a.q.gxm1, cmx) - LEAN_MAGIC;
+            sy = lean_cell_biased(__ldg(ys + n), a.q.y_lo, a.q.y_rng, a.q.r_y_rng, a.q.gym1, cmy) - LEAN_MAGIC;
+            sk = 1;
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, m);
+            sy += __shfl_xor_sync(0xffffffffu, sy, m);
+            sk += __shfl_xor_sync(0xffffffffu, sk, m);
+        }
+        if (tid == 0) {
+            sorg[0] = min(max((sk ? sx / sk : 0) - WIN / 2, 0), max(a.cx - WIN, 0));
+            sorg[1] = min(max((sk ? sy / sk : 0) - WIN / 2, 0), max(a.cy - WIN, 0));
+        }
+    }
+    for (int i = tid; i < WIN * WIN; i += NT) {
+        slo[i] = 0u;
+        shi[i] = 0u;
+        scount[i] = 0;
+    }
+    __syncthreads();
+    const int ox = sorg[0], oy = sorg[1];
+    const int oxb = ox + LEAN_MAGIC, oyb = oy + LEAN_MAGIC;
+    const long long qconst = (long long)a.scale;
+    double dot = 0.0;
+    long long cq = 0;
+    auto put = [&](float x, float y, float w, float r0) {
+        const int wx = lean_cell_biased(x, a.q.x_lo, a.q.x_rng, a.q.r_x_rng, a.q.gxm1, cmx) - oxb;
+        const int wy = lean_cell_biased(y, a.q.y_lo, a.q.y_rng, a.q.r_y_rng, a.q.gym1, cmy) - oyb;
+        if (FUSED) w = __fmul_rn(expf(__fsub_rn(w, mx)), r0);  // simulation_objects.py:296-297
+        // w * 2^s is exact in fp32 (power-of-two scale), so this equals llrint((double)w * 2^s)
+        const long long q = HASW ? __float2ll_rn(__fmul_rn(w, a.scale_f)) : qconst;
+        if ((unsigned)wx < (unsigned)WIN && (unsigned)wy < (unsigned)WIN) {
+            const int wc = wx * WIN + wy;
+            const unsigned ql = (unsigned)q, qh = (unsigned)((unsigned long long)q >> 32);
+            const unsigned old = atomicAdd(slo + wc, ql);
+            const unsigned up = qh + ((old + ql < old) ? 1u : 0u);
+            if (up) atomicAdd(shi + wc, up);
+            atomicAdd(scount + wc, 1);
+        } else {
+            const int ix = wx + ox, iy = wy + oy;
+            const int cell = ix * a.cy + iy;
+            atomicAdd(mass + cell, (unsigned long long)q);
+            atomicAdd(count + cell, 1);
+            // occupancy dot product: window cells contribute mass * p once at the flush, stray samples here
+            if (OCC && ix < a.egx && iy < a.egy) dot += (double)q * (double)__ldg(&tab[ix * a.egy + iy].x);
+        }
+        if (FUSED) {
+            // the cost clamps the cell to [0, G-1] (MotionPlanner.py:208-209), the binning to [0, G]
+            const int jx = min(wx + ox, a.egx - 1), jy = min(wy + oy, a.egy - 1);
+            const float4 e = __ldg(tab + jx * a.egy + jy);
+            const DpEval ev = dp_cost_term(e, a.q, jx, jy, x, y, w, true);
+            cq += __float2ll_rn(__fmul_rn(ev.term, a.cost_scale_f));
+        }
+    };
+    const long long g_lo = n_lo >> 2, g_hi = n_hi >> 2;  // full groups of four (chunk boundaries are multiples of four)
+    if (VW == 4) {
+        const float4 ones = make_float4(1.f, 1.f, 1.f, 1.f);
+        for (long long g = g_lo + tid; g < g_hi; g += NT) {
+            const float4 xv = __ldg(xp + g), yv = __ldg(yp + g);
+            const float4 wv = HASW ? __ldg(wp + g) : ones;
+            const float4 rv = rp ? __ldg(rp + g) : ones;
+            put(xv.x, yv.x, wv.x, rv.x);
+            put(xv.y, yv.y, wv.y, rv.y);
+            put(xv.z, yv.z, wv.z, rv.z);
+            put(xv.w, yv.w, wv.w, rv.w);
+        }
+    } else {
+        const float2 ones = make_float2(1.f, 1.f);
+        const float2 *xp2 = reinterpret_cast<const float2 *>(xp), *yp2 = reinterpret_cast<const float2 *>(yp);
+        const float2 *wp2 = reinterpret_cast<const float2 *>(wp), *rp2 = reinterpret_cast<const float2 *>(rp);
+        for (long long g = 2 * g_lo + tid; g < 2 * g_hi; g += NT) {
+            const float2 xv = __ldg(xp2 + g), yv = __ldg(yp2 + g);
+            const float2 wv = HASW ? __ldg(wp2 + g) : ones;
+            const float2 rv = rp ? __ldg(rp2 + g) : ones;
+            put(xv.x, yv.x, wv.x, rv.x);
+            put(xv.y, yv.y, wv.y, rv.y);
+        }
+    }
+    // the last block of the slice also takes the (at most three) samples behind the last full group
+    if (n_hi == a.N && n_lo < a.N && (g_hi << 2) + tid < a.N) {
+        const long long n = (g_hi << 2) + tid;
+        put(__ldg(reinterpret_cast<const float *>(xp) + n), __ldg(reinterpret_cast<const float *>(yp) + n),
+            HASW ? __ldg(reinterpret_cast<const float *>(wp) + n) : 1.f, rp ? __ldg(a.rho0 + n) : 1.f);
+    }
+    __syncthreads();
+    for (int i = tid; i < WIN * WIN; i += NT) {  // flush the window: one atomic per touched cell
+        const int c = scount[i];
+        if (c) {
+            const int wx = i / WIN, wy = i - wx * WIN;
+            const int cell = (ox + wx) * a.cy + (oy + wy);  // the window lies inside the grid (origin clamped) unless the grid is smaller
+            if (ox + wx < a.cx && oy + wy < a.cy) {
+                const unsigned long long m = ((unsigned long long)shi[i] << 32) | slo[i];
+                if (m) atomicAdd(mass + cell, m);
+                atomicAdd(count + cell, c);
+                // sum_s w_s p[cell_s] over this block's window samples = sum_cells (window mass) * p[cell]
+                if (OCC && m && ox + wx < a.egx && oy + wy < a.egy)
+                    dot += (double)(long long)m * (double)__ldg(&tab[(ox + wx) * a.egy + (oy + wy)].x);
+            }
+        }
+    }
+    if (FUSED) {  // integer sum: exact and independent of the order (one atomic per block)
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) cq += __shfl_xor_sync(0xffffffffu, cq, m);
+        if ((tid & 31) == 0) shq[tid >> 5] = cq;
+        __syncthreads();
+        if (tid == 0) {
+            long long tot = 0;
+            for (int w = 0; w < NT / 32; ++w) tot += shq[w];
+            if (tot) atomicAdd(reinterpret_cast<unsigned long long *>(a.cost_q + t), (unsigned long long)tot);
+        }
+    } else if (OCC) {  // fixed-order block reduction of the occupancy dot product
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, m);
+        if ((tid & 31) == 0) shd[tid >> 5] = dot;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < NT / 32; ++w) tot += shd[w];
+            a.partial[(size_t)t * a.B + blockIdx.x] = tot;
+        }
+    }
+}
+
 __global__ void bin_dot_finalize_kernel(const double *partial, int B, int Ts, double inv_scale, double *occ_dot) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < Ts; t += gridDim.x * blockDim.x) {
         double s = 0.0;
@@ -374,13 +549,21 @@ __global__ void normalize_apply_kernel(const float *__restrict__ rholog, const f
 
 }  // namespace
 
-// tuning / A-B knobs (read once): DP_BIN_THREADS = 1024 (default, 32 registers per thread) or 512 (64 registers),
+// tuning / A-B knobs (read once): DP_BIN_THREADS = 768 (default, 40 registers per thread, two blocks per SM), 1024 (32 registers) or 512 (64 registers),
 // DP_BIN_AGG = 0 (never aggregate), 1 (always), 2 (default: decided per block from a probe)
+static int bin_waves() {  // DP_BIN_BLOCKS_PER_SM: target number of blocks per SM over all slices (default 8; measured at the config-3 size: 2 -> 0.30 ms, 4 -> 0.25 ms, 8 -> 0.23 ms)
+    static int s_w = 0;
+    if (!s_w) {
+        const char *e = getenv("DP_BIN_BLOCKS_PER_SM");
+        s_w = (e && atoi(e) >= 1 && atoi(e) <= 64) ? atoi(e) : 8;
+    }
+    return s_w;
+}
 static void bin_knobs(int &threads, int &agg) {
     static int s_threads = 0, s_agg = 2;
     if (!s_threads) {
         const char *e = getenv("DP_BIN_THREADS");
-        s_threads = (e && atoi(e) == 512) ? 512 : 1024;
+        s_threads = (e && atoi(e) == 512) ? 512 : (e && atoi(e) == 1024) ? 1024 : 768;
         const char *g = getenv("DP_BIN_AGG");
         if (g) s_agg = atoi(g) < 0 ? 0 : (atoi(g) > 2 ? 2 : atoi(g));
     }
@@ -400,9 +583,28 @@ static int bin2d_dispatch(const BinArgs &a, bool vec, bool fused, dim3 grid, cud
         DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0, false, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
         DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<0, true, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
         DP_CUDA(cudaFuncSetAttribute(bin2d_kernel<1, false, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_lean_kernel<true, false, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_lean_kernel<false, true, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_lean_kernel<false, true, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_lean_kernel<false, false, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
+        DP_CUDA(cudaFuncSetAttribute(bin2d_lean_kernel<false, false, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_SMEM));
         attr_set = true;
     }
-    if (a.mode == 1)
+    // default: the lean kernel (no warp collectives); DP_BIN_AGG=1 or an unusual layout selects the general kernel
+    const bool lean = a.mode == 0 && vec && a.agg != 1 && a.mass && a.count && (long long)a.cx * a.cy < (1LL << 30) &&
+                      (!a.table || (long long)a.egx * a.egy < (1LL << 30));
+    if (lean) {
+        if (fused)
+            bin2d_lean_kernel<true, false, true, NT><<<grid, NT, BIN_SMEM, stream>>>(a);
+        else if (a.partial && a.w)
+            bin2d_lean_kernel<false, true, true, NT><<<grid, NT, BIN_SMEM, stream>>>(a);
+        else if (a.partial)
+            bin2d_lean_kernel<false, true, false, NT><<<grid, NT, BIN_SMEM, stream>>>(a);
+        else if (a.w)
+            bin2d_lean_kernel<false, false, true, NT><<<grid, NT, BIN_SMEM, stream>>>(a);
+        else
+            bin2d_lean_kernel<false, false, false, NT><<<grid, NT, BIN_SMEM, stream>>>(a);
+    } else if (a.mode == 1)
         bin2d_kernel<1, false, false, NT><<<grid, NT, BIN_SMEM, stream>>>(a);
     else if (fused && vec)
         bin2d_kernel<0, true, true, NT><<<grid, NT, BIN_SMEM, stream>>>(a);
@@ -455,7 +657,7 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
     a.cost_scale_f = (float)ldexp(1.0, cost_scale_log2);
     // ~2 resident blocks per SM and two waves; every block amortises one window flush over >= 8 samples per thread
     long long B = (N + NT * 8 - 1) / (NT * 8);
-    const long long target = (148LL * 4 + Ts - 1) / Ts;
+    const long long target = (148LL * bin_waves() + Ts - 1) / Ts;
     if (B > target) B = target;
     if (B * Ts > MAX_BIN_PARTIALS) B = MAX_BIN_PARTIALS / Ts;
     if (B < 1) B = 1;
@@ -475,7 +677,9 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
     const bool vec = a.mode == 0 && sx_n == 1 && (!w || sw_n == 1) && al16(x) && al16(y) && al16(w) && al16(rho0) &&
                      sx_t % 4 == 0 && (!w || sw_t % 4 == 0);
     const dim3 grid((unsigned)B, (unsigned)Ts);
-    const int rc = NT == 512 ? bin2d_dispatch<512>(a, vec, fused, grid, stream) : bin2d_dispatch<1024>(a, vec, fused, grid, stream);
+    const int rc = NT == 512   ? bin2d_dispatch<512>(a, vec, fused, grid, stream)
+                   : NT == 768 ? bin2d_dispatch<768>(a, vec, fused, grid, stream)
+                               : bin2d_dispatch<1024>(a, vec, fused, grid, stream);
     if (rc) return rc;
     if (occ_dot) {
         bin_dot_finalize_kernel<<<(Ts + 127) / 128, 128, 0, stream>>>(partial, a.B, Ts, 1.0 / a.scale, occ_dot);

@@ -11,6 +11,7 @@ Reference surface mirrored here:
 (and `bin_number` for get_density_map) are read.
 """
 import ctypes
+import sys
 import math
 
 import numpy as np
@@ -296,9 +297,9 @@ class DeviceEnv:
             h, self.handle = self.handle, None
             _lib.lib().dp_env_destroy(h)
 
-    def __del__(self):
-        import sys
-        if sys is None or sys.is_finalizing():
+    def __del__(self, _finalizing=sys.is_finalizing):
+        # at interpreter shutdown the driver context is going away with the process: nothing to release, nothing to import
+        if _finalizing():
             return
         self.close()
 

@@ -410,9 +410,48 @@ def gen_cost_init_grad(car, args):
     save("cost_init_grad.npz", **out)
 
 
+def gen_plan_motion(car, args, seeds=(0, 1)):
+    """BASELINE config 4: the reference's gradient planner, UNMODIFIED and un-attached, on the artificial environments
+    `seeds` (plan_motion.py:82-90 seeds torch / numpy the same way): MotionPlannerGrad.find_initial_traj (100 random
+    trajectories x 100 epochs on get_cost_initialize, :56-96), optimize_traj (100 epochs with the density NN, :98-160) and
+    validate_ref (the LE rollout of 500 samples x 1000 steps, :366-397).  Stored: per-epoch cost traces, the best initial
+    parameters, the final parameters and the cost dictionaries -- what tests/test_gpu_planner_real.py compares the
+    attached planner with.  About four minutes per seed on one core."""
+    rh.install()
+    with rh.ref_cwd():
+        from motion_planning.example_objects import create_mp_task
+        from motion_planning.MotionPlannerGrad import MotionPlannerGrad
+    os.makedirs("/tmp/dp_log", exist_ok=True)
+    for seed in seeds:
+        t0 = time.time()
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        with rh.ref_cwd():
+            ego = create_mp_task(args, seed)
+            planner = MotionPlannerGrad(ego, path_log="/tmp/dp_log/")
+            up_best, cost_min = planner.find_initial_traj()
+            init_costs = planner.initial_traj[1]
+            up, cost = planner.optimize_traj(up_best)
+            opt_costs = planner.improved_traj[-1][1]
+            val = planner.validate_ref(up)
+        out = {"up_init_all": planner.initial_traj[0], "up_best": up_best, "cost_min": cost_min, "up_final": up,
+               "xref0": ego.xref0, "xrefN": ego.xrefN}
+        for k, v in init_costs.items():
+            out["init_" + k] = torch.stack([c.detach() for c in v])          # (epochs, num_traj)
+        for k, v in opt_costs.items():
+            out["opt_" + k] = torch.stack([c.detach().reshape(()) for c in v])  # (epochs,)
+        for k, v in cost.items():
+            out["final_" + k] = v.detach()
+        for k, v in val.items():
+            out["val_" + k] = v.detach()
+        save("plan_motion_seed%d.npz" % seed, **out)
+        print("seed %d: %.0f s, final %s, validated %s" % (seed, time.time() - t0, {k: float(v) for k, v in cost.items()},
+                                                          {k: float(v) for k, v in val.items()}))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="weights,rollout,step,grid,env,data,planner,nn,initgrad")
+    ap.add_argument("--only", default="weights,rollout,step,grid,env,data,planner,nn,initgrad,plan")
     ap.add_argument("--env-seeds", default="0,1,2,3,4,5,6,7,8,9")
     a = ap.parse_args()
     which = a.only.split(",")
@@ -436,6 +475,8 @@ def main():
         gen_density_nn(car, args)
     if "initgrad" in which:
         gen_cost_init_grad(car, args)
+    if "plan" in which:
+        gen_plan_motion(car, args)
     print("done in %.1f s" % (time.time() - t0))
 
 

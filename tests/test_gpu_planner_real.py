@@ -1,0 +1,60 @@
+"""BASELINE config 4 on the real planner: the reference's own `MotionPlannerGrad` (unmodified, imported from the git-ignored
+copy baseline/_ref/ that baseline/make_ref.sh makes in the build container) runs `find_initial_traj`, `optimize_traj` and
+`validate_ref` (MotionPlannerGrad.py:56-160, 366-397) with every kernel-backed call bound in by `dp.attach`, and is compared
+with the SAME planner run un-attached on the CPU (goldens minted by tests/golden/make_golden.py --only plan, four minutes
+per seed).  Both runs draw the same random initial trajectories (plan_motion.py:82-90 seeding).
+
+What can be compared how: the first epochs are the same computation up to fp32 rounding (cost contract 1e-4); after that the
+two runs are two fp32 trajectories of a 200-epoch Adam optimisation with discrete phase switches (check_bounds /
+check_collision, :209-228), so trajectories that sit on a switch can separate -- the test bounds how many do, and requires the
+planner's RESULT (best initial cost, final cost terms, validated cost of the final plan) to agree."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import COST_RTOL, ROOT, golden
+
+pytestmark = pytest.mark.gpu
+
+REF = os.path.join(ROOT, "baseline", "_ref")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "systems")), reason="no baseline/_ref (run baseline/make_ref.sh)")
+@pytest.mark.parametrize("seed", [0, 1])
+def test_plan_motion_attached_vs_reference(seed, tmp_path):
+    out = str(tmp_path / "attached.npz")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_planner_attached.py"), str(seed), out],
+                       capture_output=True, text=True, timeout=1500, cwd=ROOT)
+    assert r.returncode == 0 and "PLANNER_DONE" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+    print(r.stdout.strip().splitlines()[-1])
+    a, g = np.load(out), golden("plan_motion_seed%d.npz" % seed)
+
+    # epoch 0 of the initialisation phase: identical random trajectories, costs of all 100 within the cost contract
+    rel = lambda x, y: np.abs(x - y) / np.maximum(np.abs(y), 1e-12)
+    e0 = rel(a["init_cost_sum"][0], g["init_cost_sum"][0])
+    assert e0.max() <= COST_RTOL, e0.max()
+    # the whole initialisation phase, per trajectory: how far the attached optimisation stays on the reference's path
+    dev = rel(a["init_cost_sum"], g["init_cost_sum"])                       # (epochs, num_traj)
+    on_path = (dev <= 1e-2).all(axis=0)
+    up_err = np.abs(a["up_init_all"] - g["up_init_all"]).reshape(len(on_path), -1).max(axis=1)
+    print("seed %d init phase: %d/%d trajectories within 1e-2 of the reference's cost at every epoch; median |d up| %.2e, "
+          "epoch-10 max rel dev %.2e" % (seed, on_path.sum(), len(on_path), np.median(up_err), dev[10].max()))
+    assert dev[:10].max() <= 1e-3
+    assert on_path.mean() >= 0.9
+    # the planner's choice and result
+    assert abs(float(a["cost_min"]) - float(g["cost_min"])) <= 1e-2 * abs(float(g["cost_min"])) + 1e-6
+    assert np.abs(a["up_best"] - g["up_best"]).max() <= 2e-2
+    for k in ("cost_sum", "cost_coll", "cost_goal", "cost_uref", "cost_bounds"):
+        fa, fg = float(a["final_" + k]), float(g["final_" + k])
+        va, vg = float(a["val_" + k]), float(g["val_" + k])
+        print("seed %d %-11s density phase: attached %.6f reference %.6f | validated (LE): attached %.6f reference %.6f"
+              % (seed, k, fa, fg, va, vg))
+        assert abs(fa - fg) <= 2e-2 * abs(fg) + 1e-4, k
+        assert abs(va - vg) <= 2e-2 * abs(vg) + 1e-4, k
+    assert np.abs(a["up_final"] - g["up_final"]).max() <= 5e-2
+    # and the attached planner is the fast one: reference on one host core ~57 s / ~83 s / ~97 s for the three phases
+    print("seed %d attached times: init %.1f s, density %.1f s, validate %.1f s" % (seed, float(a["time_init"]),
+                                                                               float(a["time_opt"]), float(a["time_validate"])))
