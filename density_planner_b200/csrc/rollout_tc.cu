@@ -242,16 +242,36 @@ struct SampleState {
     float x0, x1, x2, x3, x4, rho, margin;
 };
 
+// The reference row of the current time index (xref[0..4], uref[0..1]) as the chains see it.  RefS: the group's row in
+// shared memory (one reference per tile).  RefG (packed raw-data launches, BATCH == 2): every LANE has its own reference, the
+// row elements are read from global memory where they are needed (a few L1-resident sectors per step; nothing of the row
+// stays in registers across a chain).
+struct RefS {
+    const float *sm;
+    __device__ __forceinline__ float x(int k) const { return sm[k]; }
+    __device__ __forceinline__ float u(int k) const { return sm[5 + k]; }
+    __device__ __forceinline__ float4 x0123() const { return *reinterpret_cast<const float4 *>(sm); }
+};
+struct RefG {
+    const float *gx, *gu;  // &xref[0][t], &uref[0][t] of this lane's reference (t clamped to its horizon)
+    int T1, T;             // row strides
+    __device__ __forceinline__ float x(int k) const { return __ldg(gx + k * T1); }
+    __device__ __forceinline__ float u(int k) const { return __ldg(gu + k * T); }
+    __device__ __forceinline__ float4 x0123() const { return make_float4(x(0), x(1), x(2), x(3)); }
+};
+
 // error state of the controller (Controller.__call__, sytem_CAR.py:33-34) from the sample state and the reference row
-__device__ __forceinline__ float4 error_state(const SampleState &st, const float *ref) {
-    const float4 r = *reinterpret_cast<const float4 *>(ref);
+template <typename RV>
+__device__ __forceinline__ float4 error_state(const SampleState &st, const RV &ref) {
+    const float4 r = ref.x0123();
     return make_float4(st.x0 - r.x, st.x1 - r.y, __fadd_rn(__fsub_rn(st.x2, r.z), st.x4), st.x3 - r.w);
 }
 
-template <int TP, int KC, int TR, int SG, int V>
-__device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const SampleState &st, const float *ref, float (&acc)[4],
+template <int TP, int KC, int TR, int SG, int V, typename RV>
+__device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const SampleState &st, const RV &ref, float (&acc)[4],
                                       const bool fast1) {
     constexpr bool L1S = (V & 1) != 0, SH2 = (V & 2) != 0;
+    constexpr bool PACKED = sizeof(RV) != sizeof(RefS);  // per-lane references: no per-step constants shared by the group
     const int N3 = NET == 0 ? N3A : N3B;
     const float *sp = c.small + NET * SMALL_NET_FLOATS;
     const uint64_t w2h = make_bdesc(c.sbase + (NET == 0 ? OFF_W2A_HI : OFF_W2B_HI), B_LBO, B_SBO);
@@ -270,8 +290,11 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         const float4 *CB = c.sCB + NET * 64;
         // network input of U_FUNC.forward (model_CAR.py:24): (theta, v, theta - xe2, v - xe3); the last one equals the
         // reference speed for every sample and lives in the per-step constants
-        const float inz = st.x2 - __fadd_rn(__fsub_rn(st.x2, ref[2]), st.x4);
+        const float inz = st.x2 - __fadd_rn(__fsub_rn(st.x2, ref.x(2)), st.x4);
         const float2 ix = make_float2(st.x2, st.x2), iy = make_float2(st.x3, st.x3), iz = make_float2(inz, inz);
+        const float inw = PACKED ? ref.x(3) : 0.0f;  // the lane's own reference speed (packed launches)
+        const float2 iw = make_float2(inw, inw);
+        const float2 *B1P = reinterpret_cast<const float2 *>(sp + SP_B1P);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int ch = 2 * i + h;  // interleaved: the thread's four chunks are the ones it reads back below
@@ -282,10 +305,19 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int pair = 8 * ch + pq + e;
-                    const float4 wa = W1P[2 * pair], wc = CB[pair];  // wc.zw = W1[:,3] * in.w + b1 (the same for every sample)
-                    y[e] = __ffma2_rn(make_float2(wa.x, wa.y), ix, make_float2(wc.z, wc.w));
-                    y[e] = __ffma2_rn(make_float2(wa.z, wa.w), iy, y[e]);
-                    y[e] = __ffma2_rn(make_float2(wc.x, wc.y), iz, y[e]);
+                    if (PACKED) {
+                        // the same fused multiply-adds in the same order as the hoisted constant: bit-identical results
+                        const float4 wa = W1P[2 * pair], wb = W1P[2 * pair + 1];
+                        y[e] = __ffma2_rn(make_float2(wb.z, wb.w), iw, B1P[pair]);
+                        y[e] = __ffma2_rn(make_float2(wa.x, wa.y), ix, y[e]);
+                        y[e] = __ffma2_rn(make_float2(wa.z, wa.w), iy, y[e]);
+                        y[e] = __ffma2_rn(make_float2(wb.x, wb.y), iz, y[e]);
+                    } else {
+                        const float4 wa = W1P[2 * pair], wc = CB[pair];  // wc.zw = W1[:,3] * in.w + b1 (the same for every sample)
+                        y[e] = __ffma2_rn(make_float2(wa.x, wa.y), ix, make_float2(wc.z, wc.w));
+                        y[e] = __ffma2_rn(make_float2(wa.z, wa.w), iy, y[e]);
+                        y[e] = __ffma2_rn(make_float2(wc.x, wc.y), iz, y[e]);
+                    }
                 }
                 float2 t[2];
                 if (L1S) {
@@ -671,7 +703,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
     const bool logd = p.flags & DP_LOG_DENSITY, dens = p.flags & DP_DENSITY, cut = p.flags & DP_CUT;
     const bool abs_state = p.flags & DP_ABS_STATE;
     const int nd = (p.flags & DP_XY_ONLY) ? 2 : 5;
-    const long long num_tiles = BATCH ? p.R * ((p.n_per_ref + TILE - 1) / TILE) : (p.N + TILE - 1) / TILE;
+    constexpr bool PK = BATCH == 2;  // packed raw-data launches: several short references share a 128-lane tile
+    const long long num_tiles = PK      ? (p.R + TILE / p.n_per_ref - 1) / (TILE / p.n_per_ref)
+                                : BATCH ? p.R * ((p.n_per_ref + TILE - 1) / TILE)
+                                        : (p.N + TILE - 1) / TILE;
 
     // both groups run the same number of chains (a group without a tile in the last round runs a dummy one: the token
     // hand-off is symmetric)
@@ -691,10 +726,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
     const long long num_rounds = (num_tiles + NGROUPS - 1) / NGROUPS;
     for (long long round = blockIdx.x; round < num_rounds; round += gridDim.x) {
         const long long tile = round * NGROUPS + grp;
-        // sample of this thread; with several references (dp_rollout_batch) a tile belongs to exactly one of them
+        // sample of this thread; with several references (dp_rollout_batch) a tile belongs to exactly one of them (BATCH == 1)
+        // or, for references of at most 64 samples, to P = 128 / n_per_ref of them, one per block of lanes (BATCH == 2)
         long long n, ref = 0;
         bool valid;
-        if (BATCH) {
+        int Tt = 0;  // number of steps this tile runs (packed: the longest horizon among its references)
+        if (PK) {
+            const int npr = (int)p.n_per_ref, P = TILE / npr;
+            const int sub = c.s / npr, k = c.s - sub * npr;
+            ref = tile * P + sub;
+            valid = sub < P && ref < p.R;
+            if (!valid) ref = tile * P < p.R ? tile * P : p.R - 1;
+            n = ref * npr + (valid ? k : 0);
+            for (int j = 0; j < P; ++j) {
+                const long long r = tile * P + j < p.R ? tile * P + j : p.R - 1;
+                Tt = max(Tt, p.T_ref ? __ldg(p.T_ref + r) : p.T);
+            }
+        } else if (BATCH) {
             const long long tiles_per_ref = (p.n_per_ref + TILE - 1) / TILE;
             ref = tile / tiles_per_ref;
             const long long k = (tile - ref * tiles_per_ref) * TILE + c.s;
@@ -708,6 +756,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
         const long long nl = valid ? n : p.N - 1;
         const float *xref = BATCH ? p.xref + ref * 5 * T1 : p.xref, *uref = BATCH ? p.uref + ref * 2 * p.T : p.uref;
         const int T = (BATCH && p.T_ref) ? __ldg(p.T_ref + ref) : p.T;  // this reference's horizon (rows are padded to p.T)
+        if (!PK) Tt = T;
         SampleState st;
         st.x0 = __ldg(p.xe0 + nl * 5 + 0) + __ldg(xref + 0 * T1);
         st.x1 = __ldg(p.xe0 + nl * 5 + 1) + __ldg(xref + 1 * T1);
@@ -728,26 +777,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
         const float *fsrc = lane < 5 ? xref + lane * T1 : uref + (lane - 5) * p.T;
         const int flim = lane < 5 ? T : T - 1;            // last valid time index of this element's row
         group_sync(c.bar_id);  // the previous tile's last reads of sRef are done
-        if (gk < 16) {
+        if (!PK && gk < 16) {
             const int e = gk & 7, t0 = gk >> 3;
             float v = 0.0f;
             if (e < 5 && t0 <= T) v = __ldg(xref + e * T1 + t0);
             if (e >= 5 && e < 7 && t0 < T) v = __ldg(uref + (e - 5) * p.T + t0);
             sRef[t0 * 8 + e] = v;
         }
-        if (T > 0) *cb_mine = fmaf(*cb_wp, __ldg(xref + 3 * T1), *cb_bp);
+        if (!PK && T > 0) *cb_mine = fmaf(*cb_wp, __ldg(xref + 3 * T1), *cb_bp);
         group_sync(c.bar_id);
         for (int i = 0;; ++i) {
-            if (fetcher && i + 2 <= flim)
+            // packed launches: the lane's own reference row, read from global memory where it is needed; a lane whose
+            // reference is shorter than the tile's longest keeps reading its last row and neither stores nor advances
+            const RefG rvg = {xref + min(i, T), uref + max(min(i, T - 1), 0), T1, p.T};
+            if (!PK && fetcher && i + 2 <= flim)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sRef + ((i + 2) & (REF_SLOTS - 1)) * 8 + lane)),
                              "l"(fsrc + i + 2)
                              : "memory");
-            const float4 rA = *reinterpret_cast<const float4 *>(sRef + (i & (REF_SLOTS - 1)) * 8);
-            const float4 rB = *reinterpret_cast<const float4 *>(sRef + (i & (REF_SLOTS - 1)) * 8 + 4);
-            const float xr0 = rA.x, xr1 = rA.y, xr2 = rA.z, xr3 = rA.w;
+            const RefS rvs = {sRef + (i & (REF_SLOTS - 1)) * 8};
             if (i == next_store) {
                 // stored slice: the owner thread (h == 0) of each sample writes; a warp covers 32 consecutive samples per row
-                if (h == 0) {
+                if (h == 0 && (!PK || i <= T)) {
                     float r = st.rho;
                     if (cut && dens) {
                         int fl = 0;
@@ -767,12 +817,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
                                 o[p.ldn] = st.x1;
                                 if (nd == 5) { o[2 * p.ldn] = st.x2; o[3 * p.ldn] = st.x3; o[4 * p.ldn] = st.x4; }
                             } else {
-                                o[0] = st.x0 - xr0;
-                                o[p.ldn] = st.x1 - xr1;
+                                const float4 rA = PK ? rvg.x0123() : rvs.x0123();
+                                o[0] = st.x0 - rA.x;
+                                o[p.ldn] = st.x1 - rA.y;
                                 if (nd == 5) {
-                                    o[2 * p.ldn] = st.x2 - xr2;
-                                    o[3 * p.ldn] = st.x3 - xr3;
-                                    o[4 * p.ldn] = st.x4 - rB.x;
+                                    o[2 * p.ldn] = st.x2 - rA.z;
+                                    o[3 * p.ldn] = st.x3 - rA.w;
+                                    o[4 * p.ldn] = st.x4 - (PK ? rvg.x(4) : rvs.x(4));
                                 }
                             }
                         }
@@ -790,32 +841,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
                 next_store += p.stride;
                 ++slot;
             }
-            if (i == T) break;
+            if (i == Tt) break;
             // the chains take the controller's error state and network input from the sample state and the reference row
             // in shared memory where they need them (nothing but the state stays in registers across a chain)
-            const float *ref = sRef + (i & (REF_SLOTS - 1)) * 8;
             float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             bool fast1 = false;
             if (V & 1) {
                 // bound of every scaled layer-1 pre-activation of this sample and step (both nets); the sign-free sigmoid
                 // with a shared reciprocal is exact while 2^-y of the sharing arguments multiply to a normal number
                 const float *bnd = c.small + SP_BND;
-                const float inz = st.x2 - __fadd_rn(__fsub_rn(st.x2, ref[2]), st.x4);
-                const float B = fmaf(bnd[0], fabsf(st.x2), fmaf(bnd[1], fabsf(st.x3), fmaf(bnd[2], fabsf(inz), fmaf(bnd[3], fabsf(ref[3]), bnd[4]))));
+                const float r2 = PK ? rvg.x(2) : rvs.x(2), r3 = PK ? rvg.x(3) : rvs.x(3);
+                const float inz = st.x2 - __fadd_rn(__fsub_rn(st.x2, r2), st.x4);
+                const float B = fmaf(bnd[0], fabsf(st.x2), fmaf(bnd[1], fabsf(st.x3), fmaf(bnd[2], fabsf(inz), fmaf(bnd[3], fabsf(r3), bnd[4]))));
                 fast1 = __all_sync(0xffffffffu, B < ((V & 2) ? 62.5f : 31.0f));
             }
 #pragma unroll 1
             for (int net = 0; net < 2; ++net) {  // net a, then net b; the two TMEM regions swap roles
                 const uint32_t A = net == 0 ? R0 : R1, Dd = net == 0 ? R1 : R0;
                 c.RA = A; c.RD = Dd; c.ra = A + lane_off; c.rd = Dd + lane_off;
-                chain<TP, KC, TR, SG, V>(c, ph, net, st, ref, acc, fast1);
+                if (PK)
+                    chain<TP, KC, TR, SG, V>(c, ph, net, st, rvg, acc, fast1);
+                else
+                    chain<TP, KC, TR, SG, V>(c, ph, net, st, rvs, acc, fast1);
             }
             // exchange the partial head sums of the two feature halves (fixed order: both threads get identical totals)
             float *mine = sPart + h * 4 * TILE + c.s;
             mine[0 * TILE] = acc[0]; mine[1 * TILE] = acc[1]; mine[2 * TILE] = acc[2]; mine[3 * TILE] = acc[3];
-            if (i + 1 < T) *cb_mine = fmaf(*cb_wp, sRef[((i + 1) & (REF_SLOTS - 1)) * 8 + 3], *cb_bp);  // every thread is past both L1 stages
+            if (!PK && i + 1 < T) *cb_mine = fmaf(*cb_wp, sRef[((i + 1) & (REF_SLOTS - 1)) * 8 + 3], *cb_bp);  // every thread is past both L1 stages
             TRACE(16);
-            asm volatile("cp.async.wait_all;" ::: "memory");  // time index i + 2 has landed (it had the whole step)
+            if (!PK) asm volatile("cp.async.wait_all;" ::: "memory");  // time index i + 2 has landed (it had the whole step)
             fence_before();
             group_sync(c.bar_id);
             TRACE(17);
@@ -824,7 +878,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(RolloutParams p
             const float pd0 = p0[2 * TILE] + p1[2 * TILE], pd1 = p0[3 * TILE] + p1[3 * TILE];
             float sn, cs;
             sincosf(st.x2, &sn, &cs);
-            sample_advance(p, st, pu0 + ref[5], pu1 + ref[6], pd0, pd1, sn, cs);
+            if (!PK || i < T) sample_advance(p, st, pu0 + (PK ? rvg.u(0) : rvs.u(0)), pu1 + (PK ? rvg.u(1) : rvs.u(1)), pd0, pd1, sn, cs);
             TRACE(18);
         }
         if (h == 0 && valid && p.clip_margin) p.clip_margin[n] = st.margin;
@@ -929,20 +983,18 @@ int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStr
     typedef void (*kern_t)(RolloutParams);
     static const kern_t kerns[4] = {rollout_tc_kernel<1, 0, 0, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0, 0, 0>,
                                     rollout_tc_kernel<2, 0, 0, 0, 0, 0>, rollout_tc_kernel<2, 1, 0, 0, 0, 0>};
-    // The production kernels [batch][SG][V]: TP = 1, K-chunked issue.  SG: sign-free layer-2 sigmoid, picked by the host when
-    // the weights bound the layer-2 pre-activations (dp_tc_prepare); V: see the top of this file (DP_TC_V, default below).
-    static const kern_t prod[2][2][4] = {
-        {{rollout_tc_kernel<1, 1, 0, 0, 0, 0>, rollout_tc_kernel<1, 1, 0, 0, 0, 1>, rollout_tc_kernel<1, 1, 0, 0, 0, 2>,
-          rollout_tc_kernel<1, 1, 0, 0, 0, 3>},
-         {rollout_tc_kernel<1, 1, 0, 0, 1, 0>, rollout_tc_kernel<1, 1, 0, 0, 1, 1>, rollout_tc_kernel<1, 1, 0, 0, 1, 2>,
-          rollout_tc_kernel<1, 1, 0, 0, 1, 3>}},
-        {{rollout_tc_kernel<1, 1, 1, 0, 0, 0>, rollout_tc_kernel<1, 1, 1, 0, 0, 1>, rollout_tc_kernel<1, 1, 1, 0, 0, 2>,
-          rollout_tc_kernel<1, 1, 1, 0, 0, 3>},
-         {rollout_tc_kernel<1, 1, 1, 0, 1, 0>, rollout_tc_kernel<1, 1, 1, 0, 1, 1>, rollout_tc_kernel<1, 1, 1, 0, 1, 2>,
-          rollout_tc_kernel<1, 1, 1, 0, 1, 3>}}};
+    // The production kernels [batch mode][SG]: TP = 1, K-chunked issue.  Batch mode: 0 one reference, 1 several references with
+    // whole tiles each, 2 several short references packed into one tile (dp_rollout_batch with n_per_ref <= 64).  SG: sign-free
+    // layer-2 sigmoid, picked by the host when the weights bound the layer-2 pre-activations (dp_tc_prepare).  V (see the top
+    // of this file) is a compile-time choice: the measured variants 1..3 were 0.5-2 % slower (profiles/r02_k1_variants_V.txt).
+    constexpr int VD = DP_TC_V_DEFAULT;
+    static const kern_t prod[3][2] = {{rollout_tc_kernel<1, 1, 0, 0, 0, VD>, rollout_tc_kernel<1, 1, 0, 0, 1, VD>},
+                                      {rollout_tc_kernel<1, 1, 1, 0, 0, VD>, rollout_tc_kernel<1, 1, 1, 0, 1, VD>},
+                                      {rollout_tc_kernel<1, 1, 2, 0, 0, VD>, rollout_tc_kernel<1, 1, 2, 0, 1, VD>}};
     static const kern_t kern_trace = rollout_tc_kernel<1, 1, 0, 1, 0, 0>;  // with the in-kernel timeline (DP_TC_TRACE)
     static int bounded_ok = -1;  // DP_TC_BOUNDED=0 forces the general tanh (A/B and test knob)
-    static int vsel = DP_TC_V_DEFAULT;
+    constexpr int vsel = DP_TC_V_DEFAULT;
+    static int pack_ok = 1;  // DP_TC_PACK=0 keeps one reference per tile (A/B and test knob)
     if (variant < 0) {
         const char *e = getenv("DP_TC_VARIANT");
         const int v = e ? atoi(e) : 110;
@@ -950,27 +1002,31 @@ int dp_launch_rollout_tc(const dp_controller *c, const RolloutParams &p, cudaStr
         variant = 2 * tp + kc;
         const char *b = getenv("DP_TC_BOUNDED");
         bounded_ok = (b && atoi(b) == 0) ? 0 : 1;
-        const char *vs = getenv("DP_TC_V");
-        if (vs) vsel = atoi(vs) & 3;
+        const char *pk = getenv("DP_TC_PACK");
+        pack_ok = (pk && atoi(pk) == 0) ? 0 : 1;
     }
     if (!attr_set[c->device & 63]) {
         for (int k = 0; k < 4; ++k)
             DP_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        for (int b = 0; b < 2; ++b)
+        for (int b = 0; b < 3; ++b)
             for (int g = 0; g < 2; ++g)
-                for (int k = 0; k < 4; ++k)
-                    DP_CUDA(cudaFuncSetAttribute(prod[b][g][k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+                DP_CUDA(cudaFuncSetAttribute(prod[b][g], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         DP_CUDA(cudaFuncSetAttribute(kern_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_set[c->device & 63] = true;
     }
     const bool batch = p.R > 1 || p.T_ref != nullptr;
+    // several references of at most 64 samples: 128 / n_per_ref of them share a tile, one block of lanes each
+    const bool packed = batch && pack_ok && p.n_per_ref >= 1 && p.n_per_ref <= TILE / 2 && p.R > 1;
+    const int bmode = packed ? 2 : (batch ? 1 : 0);
     const char *trace_path = getenv("DP_TC_TRACE");  // diagnostic: dump an in-kernel clock64 timeline of CTA 0
     // the shared reciprocal of the sign-free layer-2 sigmoid needs |y| < 31.4 (four arguments) or < 62.8 (pairs, V & 2)
     const bool bounded = bounded_ok && c->tc_l2_bound < ((vsel & 2) ? 62.8f : 31.4f);
-    const kern_t kern = (!batch && trace_path) ? kern_trace : ((!batch && variant != 1) ? kerns[variant] : prod[batch][bounded][vsel]);
+    const kern_t kern = (!batch && trace_path) ? kern_trace : ((!batch && variant != 1) ? kerns[variant] : prod[bmode][bounded]);
     RolloutParams q = p;
     q.tc = c->d_tc;
-    const long long num_tiles = (p.R > 1 || p.T_ref) ? p.R * ((p.n_per_ref + TILE - 1) / TILE) : (p.N + TILE - 1) / TILE;
+    const long long num_tiles = packed  ? (p.R + TILE / p.n_per_ref - 1) / (TILE / p.n_per_ref)
+                                : batch ? p.R * ((p.n_per_ref + TILE - 1) / TILE)
+                                        : (p.N + TILE - 1) / TILE;
     const long long want = (num_tiles + NGROUPS - 1) / NGROUPS;
     const int grid = (int)(want < c->num_sms ? want : c->num_sms);
     if (trace_path && !batch) {

@@ -6,12 +6,45 @@ Reference surface mirrored here:
   motion_planning/MotionPlanner.py       get_cost_coll:192-224
   motion_planning/MotionPlannerGrad.py   get_cost_coll_initialize:309-336
 
-The density-NN branch (use_nn=True) is evaluated for all time points in one batched torch pass (`DensityNN`); the goal /
-bounds cost terms are kernel backed (grid.get_cost_goal / get_cost_bounds).
+The density-NN branch (use_nn=True) is evaluated for all time points in one launch of the fused tcgen05 MLP kernel
+(`DensityNN`, csrc/dnn.cu); the goal / bounds cost terms are kernel backed (grid.get_cost_goal / get_cost_bounds).
 """
 import torch
 
 from . import _lib, grid as _grid
+
+
+class _DnnFunction(torch.autograd.Function):
+    """y = MLP(x) on the fused tcgen05 kernel (dp_dnn_forward); backward = gradient w.r.t. the rows x (dp_dnn_backward)."""
+
+    @staticmethod
+    def forward(ctx, x, nn):
+        L = _lib.lib()
+        dev = nn.device
+        rows = x.shape[0]
+        xc = x.detach().to(device=dev, dtype=torch.float32).contiguous()
+        y = torch.empty((rows, nn.dims[-1]), dtype=torch.float32, device=dev)
+        need = x.requires_grad
+        masks = torch.empty((rows, nn.mask_words), dtype=torch.int32, device=dev) if (need and nn.mask_words) else None
+        with torch.cuda.device(dev):
+            _lib.check(L.dp_dnn_forward(nn.handle, _lib.ptr(xc), rows, _lib.ptr(y), _lib.ptr(masks), _lib.current_stream(dev)),
+                       "dp_dnn_forward")
+        ctx.nn, ctx.masks, ctx.need = nn, masks, need
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        if not ctx.need:
+            return None, None
+        nn = ctx.nn
+        L = _lib.lib()
+        dev = nn.device
+        g = gy.to(device=dev, dtype=torch.float32).contiguous()
+        gx = torch.empty((g.shape[0], nn.dims[0]), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.dp_dnn_backward(nn.handle, _lib.ptr(g), _lib.ptr(ctx.masks), g.shape[0], _lib.ptr(gx),
+                                         _lib.current_stream(dev)), "dp_dnn_backward")
+        return gx, None
 
 
 class DensityNN:
@@ -19,23 +52,80 @@ class DensityNN:
     prediction time points in one batched pass instead of one call per time point
     (simulation_objects.py:280-287 calls get_nn_prediction 101 times; density_training/utils.py:161-180).
 
-    Plain torch on the caller's device (cuBLAS GEMMs on the GPU; a stock dense MLP, SURVEY section 8f row 2 -- not one of
-    the hand-written kernels), differentiable w.r.t. `up` and `xe0` like the reference's branch."""
+    backend "kernel" (default): the fused tcgen05 kernel csrc/dnn.cu through dp_dnn_forward / dp_dnn_backward (all layers per
+    128-row tile on the SM, split-fp16 operands with fp32-level accuracy), differentiable w.r.t. the rows, i.e. w.r.t. `up` and
+    `xe0` like the reference's branch.  It needs a B200 and raises without one -- there is no CPU fallback.
+    backend "torch": the same batched formulation in plain torch (addmm) -- the cross-check the CPU tests replay against the
+    reference golden, and the route for the one configuration the kernel does not mirror (tanh activation)."""
 
-    def __init__(self, weights=None, device=None, activation="relu"):
+    def __init__(self, weights=None, device=None, activation="relu", backend="kernel"):
+        import ctypes
         import os
         import numpy as np
         if activation not in ("relu", "tanh"):
             raise _lib.DensityPlannerError("DensityNN mirrors the reference's MLP with relu or tanh (got %r)" % (activation,))
+        if backend not in ("kernel", "torch"):
+            raise _lib.DensityPlannerError("DensityNN backend is 'kernel' or 'torch' (got %r)" % (backend,))
         self.activation = activation
         if weights is None:
             weights = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "density_nn_default.npz")
         z = np.load(weights) if isinstance(weights, str) else weights
         n_layers = len([k for k in z.keys() if k.endswith(".weight")])
-        dev = torch.device(device) if device is not None else torch.device("cpu")
-        self.W = [torch.from_numpy(np.asarray(z["linear_list.%d.weight" % i], dtype="float32")).to(dev) for i in range(n_layers)]
-        self.b = [torch.from_numpy(np.asarray(z["linear_list.%d.bias" % i], dtype="float32")).to(dev) for i in range(n_layers)]
+        Wn = [np.ascontiguousarray(np.asarray(z["linear_list.%d.weight" % i], dtype="float32")) for i in range(n_layers)]
+        bn = [np.ascontiguousarray(np.asarray(z["linear_list.%d.bias" % i], dtype="float32")) for i in range(n_layers)]
+        self.dims = [int(Wn[0].shape[1])] + [int(w.shape[0]) for w in Wn]
+        self.handle, self.mask_words = None, 0
+        if backend == "kernel" and activation == "tanh":
+            backend = "torch"  # the kernel mirrors the reference's default (ReLU); a tanh model keeps the batched torch pass
+        self.backend = backend
+        if backend == "kernel":
+            if device is None or torch.device(device).type != "cuda":
+                if not torch.cuda.is_available():
+                    raise _lib.DensityPlannerError("DensityNN(backend='kernel') needs a B200; there is no CPU fallback "
+                                                   "(backend='torch' is the CPU cross-check formulation)")
+                device = torch.device("cuda", torch.cuda.current_device())
+            dev = torch.device(device)
+            if dev.index is None:
+                dev = torch.device("cuda", torch.cuda.current_device())
+            L = _lib.lib()
+            wp = (ctypes.c_void_p * n_layers)(*[w.ctypes.data for w in Wn])
+            bp = (ctypes.c_void_p * n_layers)(*[b.ctypes.data for b in bn])
+            dims = (ctypes.c_int * (n_layers + 1))(*self.dims)
+            h = ctypes.c_void_p()
+            _lib.check(L.dp_dnn_create(wp, bp, dims, n_layers, dev.index, ctypes.byref(h)), "dp_dnn_create")
+            self.handle = h
+            mw = ctypes.c_int()
+            _lib.check(L.dp_dnn_mask_words(h, ctypes.byref(mw)), "dp_dnn_mask_words")
+            self.mask_words = int(mw.value)
+        else:
+            dev = torch.device(device) if device is not None else torch.device("cpu")
+        self.W = [torch.from_numpy(w).to(dev) for w in Wn]
+        self.b = [torch.from_numpy(b).to(dev) for b in bn]
         self.device = dev
+
+    def close(self):
+        if getattr(self, "handle", None):
+            h, self.handle = self.handle, None
+            _lib.lib().dp_dnn_destroy(h)
+
+    def __del__(self, _finalizing=__import__("sys").is_finalizing):
+        if _finalizing():
+            return
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def mlp(self, x):
+        """rows (R, 31) -> (R, 6)."""
+        if x.shape[1] != self.dims[0]:
+            raise _lib.DensityPlannerError("the density NN expects %d inputs per row, got %d" % (self.dims[0], x.shape[1]))
+        if self.backend == "kernel":
+            return _DnnFunction.apply(x, self)
+        act = torch.relu if self.activation == "relu" else torch.tanh
+        for i in range(len(self.W) - 1):
+            x = act(torch.addmm(self.b[i], x, self.W[i].t()))
+        return torch.addmm(self.b[-1], x, self.W[-1].t())
 
     def predict(self, xe0, xref0, up, t_vec):
         """xe0 (N,5), xref0 (5,), up (1,2,10) or flat (20,), t_vec (Tn,) -> xe (N,5,Tn), rholog (N,1,Tn).
@@ -49,14 +139,10 @@ class DensityNN:
         t = t_vec.to(dev, torch.float32)
         rows = torch.cat((head.unsqueeze(0).expand(Tn, -1, -1), t.reshape(Tn, 1, 1).expand(-1, N, -1),
                           upf.unsqueeze(0).expand(Tn, -1, -1)), dim=2).reshape(Tn * N, -1)                # (Tn*N, 31)
-        x = rows
-        if x.shape[1] != self.W[0].shape[1]:
+        if rows.shape[1] != self.dims[0]:
             raise _lib.DensityPlannerError("the density NN expects %d inputs per row, the discr10 row layout has %d"
-                                           % (self.W[0].shape[1], x.shape[1]))
-        act = torch.relu if self.activation == "relu" else torch.tanh
-        for i in range(len(self.W) - 1):
-            x = act(torch.addmm(self.b[i], x, self.W[i].t()))
-        y = torch.addmm(self.b[-1], x, self.W[-1].t()).reshape(Tn, N, -1)                                # (Tn, N, 6)
+                                           % (self.dims[0], rows.shape[1]))
+        y = self.mlp(rows).reshape(Tn, N, -1)                                                            # (Tn, N, 6)
         return y[:, :, :5].permute(1, 2, 0), y[:, :, 5:6].permute(1, 2, 0)
 
 

@@ -282,6 +282,26 @@ int dp_pipeline_copy_slices(const dp_pipeline *p, float *xy_dev, float *l_dev, v
 int dp_rollout_fused(dp_pipeline *p, const float *xe0, const float *rho0, const float *xref, const float *uref, float dt,
                      int64_t N, int64_t *ibuf_host, double *out3_host);
 
+/*
+ * The density-predictor MLP of the planner's density phase: density_training/utils.py:8-40
+ * (NeuralNetwork, nn_type MLP, ReLU) as evaluated by get_nn_prediction (:161-180), which EgoVehicle.predict_density calls
+ * once per prediction time point (motion_planning/simulation_objects.py:280-287).  All rows (time points x samples) of one
+ * call run through the whole layer stack in ONE fused tcgen05 kernel (csrc/dnn.cu); the backward call returns the gradient
+ * w.r.t. the input rows (the planner differentiates w.r.t. the input parameters, the weights are frozen).
+ *   weights[l] host fp32 [dims[l+1]][dims[l]] (torch Linear.weight layout), biases[l] host fp32 [dims[l+1]],
+ *   l = 0 .. n_layers-1, ReLU after every layer but the last; n_layers <= 8, every width <= 160.
+ *   x dev [rows][dims[0]] -> y dev [rows][dims[n_layers]]
+ *   masks dev uint32 [rows][dp_dnn_mask_words()] or NULL: ReLU sign bits, written by forward, read by backward
+ *   gy dev [rows][dims[n_layers]] -> gx dev [rows][dims[0]]
+ */
+typedef struct dp_dnn dp_dnn;
+int dp_dnn_create(const float *const *weights, const float *const *biases, const int *dims, int n_layers, int device,
+                  dp_dnn **out);
+void dp_dnn_destroy(dp_dnn *h);
+int dp_dnn_mask_words(const dp_dnn *h, int *words_per_row);
+int dp_dnn_forward(const dp_dnn *h, const float *x, int64_t rows, float *y, uint32_t *masks, void *stream);
+int dp_dnn_backward(const dp_dnn *h, const float *gy, const uint32_t *masks, int64_t rows, float *gx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

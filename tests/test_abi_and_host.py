@@ -132,15 +132,16 @@ def test_product_does_not_import_oracle():
 
 def test_density_nn_batched_matches_reference_golden():
     """the density-NN branch of predict_density, all 101 time points in one batched pass, against the
-    reference's 101-call loop (forward, normalised density and the gradient w.r.t. the input parameters).  Plain torch:
-    runs on the CPU here and on the GPU in the gpu suite."""
+    reference's 101-call loop (forward, normalised density and the gradient w.r.t. the input parameters).  Here the batched
+    formulation (row layout, normaliser, autograd plumbing) in plain torch on the CPU; the product route -- the fused tcgen05
+    kernel -- replays the same golden in tests/test_gpu_planner_terms.py."""
     import types
     import torch
     import density_planner_b200 as dp
     from conftest import golden
     g = golden("density_nn.npz")
     args = dp.default_args()
-    nn = dp.DensityNN()
+    nn = dp.DensityNN(backend="torch")   # the batched formulation in plain torch: host logic, runs without a GPU
     system = types.SimpleNamespace()
     pred = dp.EgoPredictor(system, args, torch.from_numpy(g["xref0"]).reshape(1, 5, 1), torch.from_numpy(g["xe0"]).unsqueeze(-1),
                            torch.from_numpy(g["rho0"]).reshape(-1, 1, 1), density_nn=nn)

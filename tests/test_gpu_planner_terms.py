@@ -118,19 +118,69 @@ def test_attach_binds_the_kernel_backed_calls(dp, oracle, args):
     assert abs(float(cb) - float(pt["bounds_e0_m0"][0])) <= 1e-4 * float(pt["bounds_e0_m0"][0]) and not bool(inb)
 
 
-def test_density_nn_on_gpu_matches_reference_golden(dp, args):
-    """The batched density-NN branch on the GPU (cuBLAS fp32) against the reference's 101-call loop."""
+def test_density_nn_on_gpu_matches_reference_golden(dp, oracle, args):
+    """The density-NN branch on the fused tcgen05 MLP kernel (dp_dnn_forward / dp_dnn_backward, all 101 time points x 500
+    samples in one launch) against the reference's 101-call loop: states, normalised density, loss and the gradient w.r.t.
+    the input parameters -- the same golden and tolerances as the CPU cross-check in tests/test_abi_and_host.py."""
     import types
     g = golden("density_nn.npz")
     nn = dp.DensityNN(device="cuda")
+    assert nn.backend == "kernel" and nn.handle
     pred = dp.EgoPredictor(types.SimpleNamespace(), args, torch.from_numpy(g["xref0"]).reshape(1, 5, 1),
                            torch.from_numpy(g["xe0"]).unsqueeze(-1), torch.from_numpy(g["rho0"]).reshape(-1, 1, 1), density_nn=nn)
     up = torch.from_numpy(g["up"]).requires_grad_(True)
     x_traj, rho_traj = pred.predict_density(up, torch.from_numpy(g["xref_short"]), use_nn=True)
     assert x_traj.device.type == "cpu" and np.abs(x_traj.detach().numpy() - g["x_traj"]).max() < 1e-4
-    assert np.abs(rho_traj.detach()[:, 0, :].numpy() - g["rho_traj"]).max() < 1e-4 * g["rho_traj"].max()
-    (torch.from_numpy(g["w"]) * x_traj).sum().backward()
-    assert up.grad is not None and bool(torch.isfinite(up.grad).all())
+    # normalised density: the contract allows rtol 1e-3 on the log-density; the split-fp16 kernel carries ~22 mantissa bits per
+    # layer (measured: 1.2e-4 of the maximum, the plain-torch fp32 pass 0.4e-4), bound at 3e-4
+    assert np.abs(rho_traj.detach()[:, 0, :].numpy() - g["rho_traj"]).max() < 3e-4 * g["rho_traj"].max()
+    loss = (torch.from_numpy(g["w"]) * x_traj).sum() + 1e3 * (torch.from_numpy(g["wr"]).unsqueeze(1) * rho_traj).sum()
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 2e-4 * abs(float(g["loss"]))
+    # the golden differentiates through the reference integrator as well (x_traj = xe_nn + xref(up)): that part comes from the
+    # oracle's adjoint with the upstream gradient w summed over the samples (as in the CPU cross-check)
+    uref_long = np.repeat(g["up"], 100, axis=2)[:, :, :1000]
+    xref_long = oracle.xref_traj(g["xref0"], uref_long, 0.01)
+    gx = np.zeros((1, 5, 1001))
+    gx[0, :, ::10] = g["w"].sum(axis=0)
+    gu, _ = oracle.xref_traj_grad(xref_long, gx, 0.01)
+    total = up.grad.numpy() + gu.reshape(1, 2, 10, 100).sum(axis=3)
+    assert np.abs(total - g["gup"]).max() < 2e-3 * np.abs(g["gup"]).max()
+
+
+@pytest.mark.parametrize("dims", [(31, 6), (31, 150, 6), (20, 160, 33, 7), (31, 150, 150, 150, 150, 150, 150, 150, 6)])
+def test_density_nn_kernel_vs_fp64(dp, dims):
+    """dp_dnn_forward / dp_dnn_backward on random ReLU MLPs of 1, 2, 3 and 8 layers (odd widths, ragged row counts that are not
+    a multiple of the 128-row tile, more tiles than SMs) against the same network in float64: values to fp32-level accuracy
+    (three split-fp16 products per layer: ~22 mantissa bits), gradients w.r.t. the rows likewise."""
+    gen = torch.Generator().manual_seed(len(dims))
+    L = len(dims) - 1
+    z = {}
+    for l in range(L):
+        z["linear_list.%d.weight" % l] = (torch.randn(dims[l + 1], dims[l], generator=gen) / dims[l] ** 0.5).numpy()
+        z["linear_list.%d.bias" % l] = (0.1 * torch.randn(dims[l + 1], generator=gen)).numpy()
+    nn = dp.DensityNN(weights=z, device="cuda")
+    for rows in (1, 127, 128, 1000, 148 * 128 * 2 + 77):
+        x = torch.randn(rows, dims[0], generator=gen)
+        xc = x.cuda().requires_grad_(True)
+        y = nn.mlp(xc)
+        w = torch.randn(rows, dims[-1], generator=gen)
+        (y * w.cuda()).sum().backward()
+        xd = x.double().requires_grad_(True)
+        h = xd
+        for l in range(L):
+            h = torch.addmm(torch.from_numpy(z["linear_list.%d.bias" % l]).double(), h, torch.from_numpy(z["linear_list.%d.weight" % l]).double().t())
+            if l < L - 1:
+                h = torch.relu(h)
+        (h * w.double()).sum().backward()
+        err = float((y.detach().cpu().double() - h.detach()).abs().max()) / float(h.detach().abs().max())
+        # a pre-activation within rounding of zero may take the other ReLU branch in fp32: such rows (a handful in 40 M
+        # pre-activations) differ by a whole path; bound their number, and check everything else at fp32 level
+        grow = (xc.grad.cpu().double() - xd.grad).abs().max(dim=1).values / float(xd.grad.abs().max())
+        flipped = int((grow > 1e-5).sum())
+        # measured on the 8-layer stack: 3.7e-6 (values), 4.4e-6 (gradients) of the maximum -- about 1.3e-6 per layer
+        assert err < 1e-5 and flipped <= max(2, rows // 2000), (dims, rows, err, flipped, float(grow.max()))
+    nn.close()
 
 
 @pytest.mark.parametrize("seed", [0, 1])
