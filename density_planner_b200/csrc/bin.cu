@@ -559,6 +559,14 @@ static int bin_waves() {  // DP_BIN_BLOCKS_PER_SM: target number of blocks per S
     }
     return s_w;
 }
+static long long bin_min_samples() {  // DP_BIN_MIN_SAMPLES: fewest samples a block is given (default 8 per thread of a 768-thread block)
+    static long long s_m = 0;
+    if (!s_m) {
+        const char *e = getenv("DP_BIN_MIN_SAMPLES");
+        s_m = (e && atoll(e) >= 1024) ? atoll(e) : 6144;
+    }
+    return s_m;
+}
 static void bin_knobs(int &threads, int &agg) {
     static int s_threads = 0, s_agg = 2;
     if (!s_threads) {
@@ -656,7 +664,8 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
     a.lmax = lmax; a.rho0 = rho0; a.cost_q = cost_q;
     a.cost_scale_f = (float)ldexp(1.0, cost_scale_log2);
     // ~2 resident blocks per SM and two waves; every block amortises one window flush over >= 8 samples per thread
-    long long B = (N + NT * 8 - 1) / (NT * 8);
+    // every block pays for zeroing and flushing its 77 KB window: at least bin_min_samples() samples per block
+    long long B = (N + bin_min_samples() - 1) / bin_min_samples();
     const long long target = (148LL * bin_waves() + Ts - 1) / Ts;
     if (B > target) B = target;
     if (B * Ts > MAX_BIN_PARTIALS) B = MAX_BIN_PARTIALS / Ts;
