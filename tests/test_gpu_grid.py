@@ -93,6 +93,36 @@ def test_binning_counts_exact_and_order_free(dp, oracle, args):
     assert np.abs(got - ref).max() < 1e-6
 
 
+@pytest.mark.parametrize("N", [1, 3, 4, 5, 131, 4099])
+def test_binning_small_and_stray_samples(dp, oracle, args, N):
+    """The lean binning kernel on tiny, ragged sample counts (fewer samples than one vector load, tails of one to three) with
+    samples far outside the grid on either side (clamped to the border cells 0 / G like pred2grid) and exactly on cell
+    boundaries: counts bit-exact against the oracle, mass against a float64 accumulation."""
+    from density_planner_b200 import _lib, grid as G
+    rs = np.random.RandomState(N)
+    x = rs.normal(0.0, 2.0, N).astype(np.float32)
+    y = rs.normal(-5.0, 6.0, N).astype(np.float32)
+    x[::7] = np.float32(1e6)
+    y[::5] = np.float32(-1e6)
+    x[1::11] = np.float32(-12.0) + np.float32(0.05)   # half-cell points of the 0.1 m grid
+    w = rs.uniform(0, 1, N).astype(np.float32)
+    spec = _lib.BinSpec()
+    spec.mode = 0
+    spec.geom = G._geom(args)
+    spec.mass_scale_log2 = G.mass_scale_log2(N, 1.0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    xt, yt, wt = (torch.from_numpy(a).cuda() for a in (x, y, w))
+    mass, cnt = G.bin2d_raw(spec, xt, yt, wt, N, 1, (1, 0), (1, 0), dev)
+    assert int(cnt.sum()) == N
+    gx, gy = oracle.pos2gridpos(x, y)
+    ref_c = np.zeros((242, 402), np.int64)
+    ref_m = np.zeros((242, 402))
+    np.add.at(ref_c, (np.clip(gx, 0, 241), np.clip(gy, 0, 401)), 1)
+    np.add.at(ref_m, (np.clip(gx, 0, 241), np.clip(gy, 0, 401)), w.astype(np.float64))
+    assert (cnt[0].cpu().numpy() == ref_c).all()
+    assert np.abs(mass[0].cpu().numpy() / 2.0 ** spec.mass_scale_log2 - ref_m).max() < 1e-6
+
+
 def test_binning_fused_occupancy_dot(dp, args):
     """dp_bin2d_occ: time-sliced binning (shared-memory window + global fall-back) equals the slice-by-slice binning, and
     the fused obstacle-grid dot product equals sum_cells mass * grid computed from the grids afterwards."""
