@@ -220,7 +220,11 @@ def run_reference_arm(opts):
     base = None
     times = []
     budget = 6.0 if opts.steps > 1 else 12.0
-    use_ref = cpu_reference_rate(target_seconds=2.0) is not None  # the reference itself when its tree is on the box
+    try:  # the reference itself when its tree is on the box (and importable there), else the C port of its algorithm
+        use_ref = cpu_reference_rate(target_seconds=2.0) is not None
+    except Exception as exc:  # noqa: BLE001 -- a broken copy must not take the CPU arm down
+        print("bench.py: the reference under baseline/_ref could not be run (%r); timing the C port instead" % (exc,), file=sys.stderr)
+        use_ref = False
     for i in range(opts.warmup + opts.steps):
         if use_ref:
             base, units, dt = cpu_reference_rate(target_seconds=budget)
@@ -601,7 +605,11 @@ def main():
             "collision_cost_evals_per_s": cfg3["cost_fwd"]["evals_per_s"] if cfg3 else None,
             "collision_cost_config3": cfg3, "rawdata_config1": cfg1, "checks": checks}
     if not opts.no_cpu_baseline and world == 1:
-        ref = cpu_reference_rate()
+        try:
+            ref = cpu_reference_rate()
+        except Exception as exc:  # noqa: BLE001
+            print("bench.py: the reference under baseline/_ref could not be run (%r)" % (exc,), file=sys.stderr)
+            ref = None
         port, _, _ = cpu_oracle_rate()
         if ref is not None:  # the reference's own PyTorch path; the C port beside it
             base = ref[0]

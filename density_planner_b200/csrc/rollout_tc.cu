@@ -106,6 +106,9 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 #ifndef DP_TC_V_DEFAULT
 #define DP_TC_V_DEFAULT 0   // production variant V (see above); DP_TC_V overrides it at run time
 #endif
+#ifndef DP_TIE
+#define DP_TIE 0   // bit 0: chain the four tanh groups of a layer-1 chunk (see tc_ptx.cuh), bit 1: the same in the layer-2 epilogue
+#endif
 #ifndef DP_SPLIT
 #define DP_SPLIT 2   // 0: F2FP + two conversions back, 1: mantissa truncation (LOP3), 2: mixed-precision FHADD (default)
 #endif
@@ -295,6 +298,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         const float inw = PACKED ? ref.x(3) : 0.0f;  // the lane's own reference speed (packed launches)
         const float2 iw = make_float2(inw, inw);
         const float2 *B1P = reinterpret_cast<const float2 *>(sp + SP_B1P);
+        float tie1 = 0.0f;  // DP_TIE & 1: R (or the product) of the previous group; tie1 * 0 is folded into iz below
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int ch = 2 * i + h;  // interleaved: the thread's four chunks are the ones it reads back below
@@ -302,6 +306,11 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
 #pragma unroll
             for (int pq = 0; pq < 8; pq += 2) {
                 float2 y[2];
+                float2 izg = iz;
+                if ((DP_TIE & 1) && !L1S) {
+                    const float z1 = fmaf(tie1, 0.0f, inz);  // = inz; makes this group's pre-activations wait for the previous group
+                    izg = make_float2(z1, z1);
+                }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int pair = 8 * ch + pq + e;
@@ -311,12 +320,12 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                         y[e] = __ffma2_rn(make_float2(wb.z, wb.w), iw, B1P[pair]);
                         y[e] = __ffma2_rn(make_float2(wa.x, wa.y), ix, y[e]);
                         y[e] = __ffma2_rn(make_float2(wa.z, wa.w), iy, y[e]);
-                        y[e] = __ffma2_rn(make_float2(wb.x, wb.y), iz, y[e]);
+                        y[e] = __ffma2_rn(make_float2(wb.x, wb.y), izg, y[e]);
                     } else {
                         const float4 wa = W1P[2 * pair], wc = CB[pair];  // wc.zw = W1[:,3] * in.w + b1 (the same for every sample)
                         y[e] = __ffma2_rn(make_float2(wa.x, wa.y), ix, make_float2(wc.z, wc.w));
                         y[e] = __ffma2_rn(make_float2(wa.z, wa.w), iy, y[e]);
-                        y[e] = __ffma2_rn(make_float2(wc.x, wc.y), iz, y[e]);
+                        y[e] = __ffma2_rn(make_float2(wc.x, wc.y), izg, y[e]);
                     }
                 }
                 float2 t[2];
@@ -332,7 +341,9 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
                         t[0] = __ffma2_rn(t[0], half2v, half2v);
                         t[1] = __ffma2_rn(t[1], half2v, half2v);
                     }
-                } else
+                } else if (DP_TIE & 1)
+                    tanh4(y[0], y[1], t[0], t[1], tie1);
+                else
                     tanh4(y[0], y[1], t[0], t[1]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -389,6 +400,7 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
         // fed with r, layer 2 sees W2 h1 = 2 W2 r - rowsum(W2): factor in the scale, row sums in the bias
         const float2 *B2P = reinterpret_cast<const float2 *>(sp + (L1S ? SP_B2R : SP_B2P));
         const float2 cs = make_float2(L1S ? 2.0f * C2SCALE : C2SCALE, L1S ? 2.0f * C2SCALE : C2SCALE);
+        float tie2 = 0.0f;  // DP_TIE & 2, as in layer 1
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int ch = 4 * h + i;
@@ -397,13 +409,19 @@ __device__ __forceinline__ void chain(Ctx &c, uint32_t &ph, const int NET, const
             wait_ld();
 #pragma unroll
             for (int pq = 0; pq < 8; pq += 2) {
-                const float2 y0 = __ffma2_rn(as_f2(d[2 * pq], d[2 * pq + 1]), cs, B2P[8 * ch + pq]);
-                const float2 y1 = __ffma2_rn(as_f2(d[2 * pq + 2], d[2 * pq + 3]), cs, B2P[8 * ch + pq + 1]);
+                float2 csg = cs;
+                if ((DP_TIE & 2) && SG && !SH2) {
+                    const float c1 = fmaf(tie2, 0.0f, cs.x);  // = cs.x; this group's pre-activations wait for the previous group
+                    csg = make_float2(c1, c1);
+                }
+                const float2 y0 = __ffma2_rn(as_f2(d[2 * pq], d[2 * pq + 1]), csg, B2P[8 * ch + pq]);
+                const float2 y1 = __ffma2_rn(as_f2(d[2 * pq + 2], d[2 * pq + 3]), csg, B2P[8 * ch + pq + 1]);
                 float2 t[2];
                 // SG: the layer-2 pre-activations are bounded by the weights (dp_tc_prepare), so no |y| / sign copy is
                 // needed, and layer 3 takes r = (1 + h2) / 2 as its operand (scale and bias adjusted in R4, gate = g2 / 4
                 // made up for in R56)
                 if (SG && SH2) sigm4_pairs(y0, y1, t[0], t[1]);
+                else if (SG && (DP_TIE & 2)) sigm4_bounded(y0, y1, t[0], t[1], tie2);
                 else if (SG) sigm4_bounded(y0, y1, t[0], t[1]);
                 else tanh4(y0, y1, t[0], t[1]);
 #pragma unroll

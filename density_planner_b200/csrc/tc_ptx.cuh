@@ -158,6 +158,25 @@ __device__ __forceinline__ float2 copysign2(const float2 mag, const float2 sgn) 
     return make_float2(__uint_as_float(__float_as_uint(mag.x) | (__float_as_uint(sgn.x) & 0x80000000u)),
                        __uint_as_float(__float_as_uint(mag.y) | (__float_as_uint(sgn.y) & 0x80000000u)));
 }
+// DP_TIE (A/B knob, rollout_tc.cu): the shared reciprocal R (DP_TIE_ON == 0) or the product it is taken of (== 1) of one
+// group of four is handed to the caller, which folds `R * 0` into an operand of the NEXT group's pre-activations.  The value
+// is unchanged (R is finite), but the next group's MUFU.EX2 now depend on this group: ptxas can no longer hoist all sixteen
+// EX2 of a chunk into one burst that serialises the four warps of a scheduler on the XU pipe.
+#ifndef DP_TIE_ON
+#define DP_TIE_ON 0
+#endif
+__device__ __forceinline__ void tanh4(const float2 yA, const float2 yB, float2 &tA, float2 &tB, float &tie) {
+    const float2 one = make_float2(1.0f, 1.0f), two = make_float2(2.0f, 2.0f), mone = make_float2(-1.0f, -1.0f);
+    const float2 aA = __fadd2_rn(make_float2(ex2_negabs(yA.x), ex2_negabs(yA.y)), one);
+    const float2 aB = __fadd2_rn(make_float2(ex2_negabs(yB.x), ex2_negabs(yB.y)), one);
+    const float2 p = __fmul2_rn(aA, aB);                       // (a0 a2, a1 a3)
+    const float R = rcp_approx(p.x * p.y);
+    tie = DP_TIE_ON ? p.x : R;
+    const float2 q = make_float2(R * p.y, R * p.x);            // (1/(a0 a2), 1/(a1 a3))
+    const float2 rA = __fmul2_rn(q, aB), rB = __fmul2_rn(q, aA);  // (1/a0, 1/a1), (1/a2, 1/a3)
+    tA = copysign2(__ffma2_rn(two, rA, mone), yA);
+    tB = copysign2(__ffma2_rn(two, rB, mone), yB);
+}
 __device__ __forceinline__ void tanh4(const float2 yA, const float2 yB, float2 &tA, float2 &tB) {
     const float2 one = make_float2(1.0f, 1.0f), two = make_float2(2.0f, 2.0f), mone = make_float2(-1.0f, -1.0f);
     const float2 aA = __fadd2_rn(make_float2(ex2_negabs(yA.x), ex2_negabs(yA.y)), one);
@@ -186,6 +205,17 @@ __device__ __forceinline__ void tanh4_bounded(const float2 yA, const float2 yB, 
 // ... and the variant that returns r = 1 / (1 + 2^-y) = (1 + tanh x) / 2 itself: a layer whose consumer is linear can take
 // r as its operand (W tanh = 2 W r - W 1: the factor and the row sums go into the consumer's scale and bias), which saves
 // the 2 r - 1 step; the gate is 1 - tanh^2 = 4 r (1 - r).
+__device__ __forceinline__ void sigm4_bounded(const float2 yA, const float2 yB, float2 &rA, float2 &rB, float &tie) {
+    const float2 one = make_float2(1.0f, 1.0f);
+    const float2 aA = __fadd2_rn(make_float2(ex2_approx(-yA.x), ex2_approx(-yA.y)), one);
+    const float2 aB = __fadd2_rn(make_float2(ex2_approx(-yB.x), ex2_approx(-yB.y)), one);
+    const float2 p = __fmul2_rn(aA, aB);
+    const float R = rcp_approx(p.x * p.y);
+    tie = DP_TIE_ON ? fminf(p.x, 3.0e38f) : R;   // the product may overflow to +inf (R = 0 then): keep the tie finite
+    const float2 q = make_float2(R * p.y, R * p.x);
+    rA = __fmul2_rn(q, aB);
+    rB = __fmul2_rn(q, aA);
+}
 __device__ __forceinline__ void sigm4_bounded(const float2 yA, const float2 yB, float2 &rA, float2 &rB) {
     const float2 one = make_float2(1.0f, 1.0f);
     const float2 aA = __fadd2_rn(make_float2(ex2_approx(-yA.x), ex2_approx(-yA.y)), one);

@@ -9,6 +9,6 @@ mkdir -p ../../build/variants
 NVCC=/usr/local/cuda/bin/nvcc
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 $NVCC -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC -Xptxas -v -ccbin /usr/bin/g++ "$@" -c rollout_tc.cu -o ../../build/variants/$name.o 2> ../../build/variants/$name.ptxas.log
-objs=$(ls *.o | grep -v rollout_tc.o)
-$NVCC $ARCH -shared -o ../../build/variants/$name.so $objs ../../build/variants/$name.o -ccbin /usr/bin/g++
+objs="api.o step.o cost.o bin.o planner.o pipeline.o dnn.o"   # the product objects (make them first)
+$NVCC $ARCH -shared -o ../../build/variants/$name.so $objs ../../build/variants/$name.o -ccbin /usr/bin/g++ 2>&1 | tail -3
 grep -A1 "ILi1ELi1ELi0ELi0ELi1" ../../build/variants/$name.ptxas.log | grep spill
