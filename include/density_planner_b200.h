@@ -86,8 +86,9 @@ int dp_rollout(const dp_controller *c, const float *xe0, const float *xref, cons
  *   xe0 dev [R*n_per_ref][5];  xref dev [R][5][T+1];  uref dev [R][2][T] (rows padded to the common T)
  *   T_ref dev int[R] or NULL: horizon of every reference (<= T; slots beyond it are left untouched)
  *   outputs as dp_rollout with N = R*n_per_ref samples, reference r owning samples [r*n_per_ref, (r+1)*n_per_ref)
- * Samples of several references share a 128-lane tile (the reference is a per-lane property), so R references of 20
- * samples fill the lanes as R*20 samples of one reference would.
+ * References of at most 64 samples are packed, 128 / n_per_ref of them per 128-lane tile (the reference row, its horizon and
+ * the reference speed are per-lane properties there), so R references of 20 samples fill 120 of 128 lanes; larger references
+ * own whole tiles.  Either way the results equal R separate dp_rollout calls bit for bit.
  */
 int dp_rollout_batch(const dp_controller *c, const float *xe0, const float *xref, const float *uref, const int *T_ref,
                      const float *rho0, float dt, int64_t R, int64_t n_per_ref, int T, unsigned flags, int stride,
