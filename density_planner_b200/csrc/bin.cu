@@ -37,6 +37,7 @@ struct BinArgs {
     int egx, egy;         // its cells per axis
     double *partial;      // [Ts][B] partial occupancy dot products or null
     int B;
+    int prefetch;         // lean kernel: L2 prefetch distance of the streamed rows in iterations (0 off; DP_BIN_PREFETCH)
     int agg;              // warp aggregation of same-cell samples before the shared atomics: 0 off, 1 on, 2 decided per block
     // fused pipeline pass (FUSED kernels, dp_pipeline_bin): the weight column holds the log-density l and the weight is
     // exp(l - lmax[t]) * rho0[n] (simulation_objects.py:296-297, before the division by the sum); the same pass
@@ -398,7 +399,13 @@ __global__ void __launch_bounds__(NT, 2) bin2d_lean_kernel(BinArgs a) {
     const long long g_lo = n_lo >> 2, g_hi = n_hi >> 2;  // full groups of four (chunk boundaries are multiples of four)
     if (VW == 4) {
         const float4 ones = make_float4(1.f, 1.f, 1.f, 1.f);
+        const long long pf = (long long)a.prefetch * NT;
         for (long long g = g_lo + tid; g < g_hi; g += NT) {
+            if (pf && g + pf < g_hi) {  // a later iteration's rows on their way into L2 while this one computes
+                dp_prefetch_l2(xp + g + pf);
+                dp_prefetch_l2(yp + g + pf);
+                if (HASW) dp_prefetch_l2(wp + g + pf);
+            }
             const float4 xv = __ldg(xp + g), yv = __ldg(yp + g);
             const float4 wv = HASW ? __ldg(wp + g) : ones;
             const float4 rv = rp ? __ldg(rp + g) : ones;
@@ -661,6 +668,14 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
     a.sx_n = sx_n; a.sx_t = sx_t; a.sw_n = sw_n; a.sw_t = sw_t; a.N = N; a.Ts = Ts;
     a.mass = mass; a.count = count;
     a.agg = agg;
+    {
+        static int s_pf = -1;
+        if (s_pf < 0) {
+            const char *pe = getenv("DP_BIN_PREFETCH");
+            s_pf = (pe && atoi(pe) >= 0 && atoi(pe) <= 8) ? atoi(pe) : 1;
+        }
+        a.prefetch = s_pf;
+    }
     a.lmax = lmax; a.rho0 = rho0; a.cost_q = cost_q;
     a.cost_scale_f = (float)ldexp(1.0, cost_scale_log2);
     // ~2 resident blocks per SM and two waves; every block amortises one window flush over >= 8 samples per thread

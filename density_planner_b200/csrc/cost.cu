@@ -4,6 +4,8 @@
 //   pos2gridpos / gridpos2pos                motion_planning/utils.py:70-116
 // HBM-bound: 12 B streamed per (sample, slice) forward (+12 B gradients), one 16-byte gather from a time-major
 // {p, gradX, gradY} table that stays L2-resident because samples cluster around the reference trajectory.
+#include <stdlib.h>
+
 #include "dp_common.cuh"
 
 namespace {
@@ -53,6 +55,7 @@ struct CostArgs {
     float *partial_max;   // [Ts][B]   max mode (-inf = no active sample)
     double *cost_samples; // [N] or null (generic kernel only)
     int B;
+    int prefetch;         // L2 prefetch distance of the streamed rows in grid-stride iterations (0 off; DP_COST_PREFETCH)
 };
 
 // (A) main path: samples contiguous (sx_n == 1).  grid (B, Ts): block (b, t) strides over the samples of slice t.
@@ -105,8 +108,8 @@ __global__ void __launch_bounds__(CB) cost_nfast_kernel(CostArgs a) {
 
 // (V) the same for 16-byte aligned rows: every thread evaluates four consecutive samples per iteration from three LDG.128
 // (x, y, rho) and writes the gradients with STG.128 -- a quarter of the memory instructions of (A) for the same bytes.
-template <bool WANT_G>
-__global__ void __launch_bounds__(CB, WANT_G ? 4 : 6) cost_vec4_kernel(CostArgs a) {
+template <bool WANT_G, int MINB>
+__global__ void __launch_bounds__(CB, MINB) cost_vec4_kernel(CostArgs a) {
     __shared__ double shd[CB / 32];
     __shared__ float shf[CB / 32];
     const int t = blockIdx.y;
@@ -118,7 +121,13 @@ __global__ void __launch_bounds__(CB, WANT_G ? 4 : 6) cost_vec4_kernel(CostArgs 
     float mx = -INFINITY;
     const long long n4 = a.N >> 2;  // full groups of four
     const long long stride = (long long)gridDim.x * CB;
+    const long long pf = a.prefetch * stride;
     for (long long g = (long long)blockIdx.x * CB + threadIdx.x; g < n4; g += stride) {
+        if (pf && g + pf < n4) {  // the rows of a later iteration on their way into L2 while this one computes
+            dp_prefetch_l2(reinterpret_cast<const float4 *>(xp) + g + pf);
+            dp_prefetch_l2(reinterpret_cast<const float4 *>(yp) + g + pf);
+            if (has_rho) dp_prefetch_l2(reinterpret_cast<const float4 *>(rp) + g + pf);
+        }
         const float4 xv = __ldg(reinterpret_cast<const float4 *>(xp) + g);
         const float4 yv = __ldg(reinterpret_cast<const float4 *>(yp) + g);
         const float4 rv = has_rho ? __ldg(reinterpret_cast<const float4 *>(rp) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -331,6 +340,14 @@ int dp_cost_coll(const dp_env *e, const float *x, const float *y, int64_t sx_n, 
     a.partial = env_ws(e)->partial;
     a.partial_max = env_ws(e)->partial_max;
     a.cost_samples = cost_samples;
+    {
+        static int s_pf = -1;  // DP_COST_PREFETCH: L2 prefetch distance in grid-stride iterations (A/B knob, default below)
+        if (s_pf < 0) {
+            const char *pe = getenv("DP_COST_PREFETCH");
+            s_pf = (pe && atoi(pe) >= 0 && atoi(pe) <= 8) ? atoi(pe) : 1;
+        }
+        a.prefetch = s_pf;
+    }
     const bool nfast = (sx_n == 1) && (!rho || sr_n == 1) && (!gx || sg_n == 1) && !cost_samples;
     if (nfast) {
         long long B = (N + CB * 4 - 1) / (CB * 4);
@@ -345,14 +362,33 @@ int dp_cost_coll(const dp_env *e, const float *x, const float *y, int64_t sx_n, 
                          (!rho || sr_t % 4 == 0) && (!gx || sg_t % 4 == 0);
         if (vec) {
             // two full waves of resident blocks over all slices (the kernel strides over the samples of its slice)
-            long long Bv = (2LL * (gx ? 4 : 6) * 148) / Ts;
+            static int s_minb = 0, s_waves = 0;  // A/B knobs: resident blocks per SM of the forward kernel, waves over all slices
+            if (!s_minb) {
+                const char *me = getenv("DP_COST_FWD_MINB");
+                s_minb = (me && (atoi(me) == 6 || atoi(me) == 8)) ? atoi(me) : 4;
+                const char *we = getenv("DP_COST_WAVES");
+                s_waves = (we && atoi(we) >= 1 && atoi(we) <= 16) ? atoi(we) : 4;
+            }
+            // Measured at the config-3 size (profiles/r02_cost_knobs.txt): four resident blocks per SM (63 registers, four
+            // evaluations in flight per thread) and just under four FULL waves of blocks over all slices -- 23 blocks per
+            // slice = 3.92 waves: 0.274 / 0.404 ms (forward / forward + backward); 24 per slice = 4.09 waves, i.e. a fifth,
+            // almost empty wave: 0.280 / 0.427 ms; two waves 0.297 / 0.427 ms; six resident blocks (39 registers) 0.294 ms.
+            const int minb = gx ? 4 : s_minb;
+            long long Bv = ((long long)s_waves * minb * 148) / Ts;
+            const long long Bmax = (N + CB * 4 - 1) / (CB * 4);  // at least one vector iteration per thread
+            if (Bv > Bmax) Bv = Bmax;
+            if (Bv * Ts > MAX_PARTIALS) Bv = MAX_PARTIALS / Ts;
             if (Bv < 1) Bv = 1;
-            if (Bv > B) Bv = B;
             a.B = (int)Bv;
+            const dim3 grid((unsigned)Bv, (unsigned)Ts);
             if (gx)
-                cost_vec4_kernel<true><<<dim3((unsigned)Bv, (unsigned)Ts), CB, 0, stream>>>(a);
+                cost_vec4_kernel<true, 4><<<grid, CB, 0, stream>>>(a);
+            else if (minb == 4)
+                cost_vec4_kernel<false, 4><<<grid, CB, 0, stream>>>(a);
+            else if (minb == 8)
+                cost_vec4_kernel<false, 8><<<grid, CB, 0, stream>>>(a);
             else
-                cost_vec4_kernel<false><<<dim3((unsigned)Bv, (unsigned)Ts), CB, 0, stream>>>(a);
+                cost_vec4_kernel<false, 6><<<grid, CB, 0, stream>>>(a);
         }
         else
             cost_nfast_kernel<<<dim3((unsigned)B, (unsigned)Ts), CB, 0, stream>>>(a);

@@ -189,6 +189,22 @@ __device__ __forceinline__ int dp_cell(float p, float lo, float range, float r_r
     const float q = __fmul_rn(GUARD ? dp_div(a, range, r_range) : dp_div_fast(a, range, r_range), gm1);
     return __float2int_rn(__fadd_rn(q, 0.001f));  // round-half-even like torch.round; values are far from int overflow
 }
+// The same cell, clamped to [0, hi], as an exactly representable FLOAT and as an int, without the XU-pipe conversions
+// (F2I for the cell, I2F for the gradient-shifted grid position of the cost): clamp in float, then the magic-number add
+// (t + 1.5 * 2^23 carries rn(t) in its low mantissa bits, ties to even like cvt.rni / torch.round).  Rounding is monotone and
+// fixes the integers 0 and hi, so rn(clamp(t, 0, hi)) = clamp(rn(t), 0, hi): identical cells (NaN -> 0 like F2I).
+__device__ __forceinline__ void dp_cell_clamped(float p, float lo, float range, float r_range, float gm1, float hi, int &cell,
+                                                float &cell_f) {
+    const float q = __fmul_rn(dp_div_fast(__fsub_rn(p, lo), range, r_range), gm1);
+    const float t = fminf(fmaxf(__fadd_rn(q, 0.001f), 0.0f), hi);
+    const float m = __fadd_rn(t, 12582912.0f);
+    cell = __float_as_int(m) - 0x4B400000;
+    cell_f = __fsub_rn(m, 12582912.0f);
+}
+
+// L2 prefetch of the line holding p (a hint: the streaming kernels issue it one grid-stride iteration ahead)
+__device__ __forceinline__ void dp_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // gridpos2pos for one coordinate (motion_planning/utils.py:100-116)
 template <bool GUARD = true>
 __device__ __forceinline__ float dp_pos(float g, float lo, float range, float gm1, float r_gm1) {
@@ -203,13 +219,13 @@ struct DpEval {
 };
 
 // the terms of one evaluation from the gathered table entry e = {p, gradX, gradY, 0} of the (clamped) cell (ix, iy)
-__device__ __forceinline__ DpEval dp_cost_term(const float4 e, const DpGeom &q, int ix, int iy, float x, float y, float rho,
-                                               bool has_rho) {
+__device__ __forceinline__ DpEval dp_cost_term_f(const float4 e, const DpGeom &q, float fx, float fy, float x, float y, float rho,
+                                                 bool has_rho) {
     DpEval r;
     r.active = (e.y != 0.0f) || (e.z != 0.0f);  // :213-214
     // des_gridpos = gridpos + 100 * grad ; gridpos2pos ; squared distance (:215-218), each op rounded like torch
-    const float dgx = __fadd_rn(__int2float_rn(ix), __fmul_rn(100.0f, e.y));
-    const float dgy = __fadd_rn(__int2float_rn(iy), __fmul_rn(100.0f, e.z));
+    const float dgx = __fadd_rn(fx, __fmul_rn(100.0f, e.y));
+    const float dgy = __fadd_rn(fy, __fmul_rn(100.0f, e.z));
     const float dpx = dp_pos<false>(dgx, q.x_lo, q.x_rng, q.gxm1, q.r_gxm1);
     const float dpy = dp_pos<false>(dgy, q.y_lo, q.y_rng, q.gym1, q.r_gym1);
     const float ex = __fsub_rn(dpx, x), ey = __fsub_rn(dpy, y);
@@ -222,12 +238,17 @@ __device__ __forceinline__ DpEval dp_cost_term(const float4 e, const DpGeom &q, 
     return r;
 }
 
+__device__ __forceinline__ DpEval dp_cost_term(const float4 e, const DpGeom &q, int ix, int iy, float x, float y, float rho,
+                                               bool has_rho) {
+    return dp_cost_term_f(e, q, __int2float_rn(ix), __int2float_rn(iy), x, y, rho, has_rho);
+}
+
 __device__ __forceinline__ DpEval dp_cost_eval(const float4 *__restrict__ table, const DpGeom &q, int t, float x, float y, float rho,
                                                bool has_rho) {
-    int ix = dp_cell<false>(x, q.x_lo, q.x_rng, q.r_x_rng, q.gxm1);
-    int iy = dp_cell<false>(y, q.y_lo, q.y_rng, q.r_y_rng, q.gym1);
-    ix = min(max(ix, 0), q.gx - 1);  // :208-209
-    iy = min(max(iy, 0), q.gy - 1);
+    int ix, iy;
+    float fx, fy;
+    dp_cell_clamped(x, q.x_lo, q.x_rng, q.r_x_rng, q.gxm1, q.gxm1, ix, fx);  // clamp to [0, G-1] (:208-209)
+    dp_cell_clamped(y, q.y_lo, q.y_rng, q.r_y_rng, q.gym1, q.gym1, iy, fy);
     const float4 e = __ldg(table + ((size_t)t * q.gx + ix) * q.gy + iy);  // {p, gradX, gradY, 0}
-    return dp_cost_term(e, q, ix, iy, x, y, rho, has_rho);
+    return dp_cost_term_f(e, q, fx, fy, x, y, rho, has_rho);
 }
