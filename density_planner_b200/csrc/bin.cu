@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(NT, 2) bin2d_kernel(BinArgs a) {
                         // the cost clamps the cell to [0, G-1] (MotionPlanner.py:208-209), the binning to [0, G]
                         const int jx = min(ix, a.egx - 1), jy = min(iy, a.egy - 1);
                         const float4 e = __ldg(tab + (size_t)jx * a.egy + jy);
-                        const DpEval ev = dp_cost_term(e, a.q, jx, jy, x, y, w, true);
+                        const DpEval ev = dp_cost_term(e, x, y, w, true);
                         cq += __float2ll_rn(__fmul_rn(ev.term, a.cost_scale_f));
                     } else if (ix < a.egx && iy < a.egy) {
                         dot += (double)q * (double)__ldg(&tab[(size_t)ix * a.egy + iy].x);
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(NT, 2) bin2d_lean_kernel(BinArgs a) {
             // the cost clamps the cell to [0, G-1] (MotionPlanner.py:208-209), the binning to [0, G]
             const int jx = min(wx + ox, a.egx - 1), jy = min(wy + oy, a.egy - 1);
             const float4 e = __ldg(tab + jx * a.egy + jy);
-            const DpEval ev = dp_cost_term(e, a.q, jx, jy, x, y, w, true);
+            const DpEval ev = dp_cost_term(e, x, y, w, true);
             cq += __float2ll_rn(__fmul_rn(ev.term, a.cost_scale_f));
         }
     };
@@ -681,7 +681,10 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
     // ~2 resident blocks per SM and two waves; every block amortises one window flush over >= 8 samples per thread
     // every block pays for zeroing and flushing its 77 KB window: at least bin_min_samples() samples per block
     long long B = (N + bin_min_samples() - 1) / bin_min_samples();
-    const long long target = (148LL * bin_waves() + Ts - 1) / Ts;
+    // rounded DOWN: the blocks of all slices then fit the intended number of full waves (two resident blocks per SM); one
+    // block more per slice puts an almost empty wave at the end (measured on the cost kernels, profiles/r02_cost_knobs.txt)
+    long long target = (148LL * bin_waves()) / Ts;
+    if (target < 1) target = 1;
     if (B > target) B = target;
     if (B * Ts > MAX_BIN_PARTIALS) B = MAX_BIN_PARTIALS / Ts;
     if (B < 1) B = 1;

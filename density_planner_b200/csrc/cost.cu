@@ -233,8 +233,12 @@ __global__ void cost_finalize_kernel(const double *partial, const float *partial
 }
 
 __global__ void env_pack_kernel(const float *__restrict__ grid, const float *__restrict__ gradx,
-                                const float *__restrict__ grady, int G0, int G1, int Tg, float4 *__restrict__ table) {
+                                const float *__restrict__ grady, int G0, int G1, int Tg, Geom q, float4 *__restrict__ table) {
     // input (G0,G1,Tg) time innermost; output [t][ix][iy].  Tile-transposed through shared memory.
+    // Everything of the collision cost that depends on the CELL alone is evaluated here, once per cell instead of once per
+    // sample: des_gridpos = gridpos + 100 * grad and des_pos = gridpos2pos(des_gridpos) (MotionPlanner.py:215-217), op for op
+    // in fp32 as the per-sample code did (so the costs and gradients stay bit-identical), and the activity test (:213-214).
+    // Entry = {p, des_pos_x, des_pos_y, active ? 1 : 0}.
     __shared__ float4 tile[32][33];
     const long long cell0 = (long long)blockIdx.x * 32;  // cell = ix*G1 + iy
     const int t0 = blockIdx.y * 32;
@@ -246,7 +250,13 @@ __global__ void env_pack_kernel(const float *__restrict__ grid, const float *__r
             const int t = t0 + tl;
             if (cell < cells && t < Tg) {
                 const size_t i = (size_t)cell * Tg + t;
-                tile[c][tl] = make_float4(grid[i], gradx[i], grady[i], 0.0f);
+                const float gX = gradx[i], gY = grady[i];
+                const int ix = (int)(cell / G1), iy = (int)(cell - (long long)ix * G1);
+                const float dgx = __fadd_rn(__int2float_rn(ix), __fmul_rn(100.0f, gX));
+                const float dgy = __fadd_rn(__int2float_rn(iy), __fmul_rn(100.0f, gY));
+                tile[c][tl] = make_float4(grid[i], dp_pos<false>(dgx, q.x_lo, q.x_rng, q.gxm1, q.r_gxm1),
+                                          dp_pos<false>(dgy, q.y_lo, q.y_rng, q.gym1, q.r_gym1),
+                                          (gX != 0.0f || gY != 0.0f) ? 1.0f : 0.0f);
             }
         }
     }
@@ -297,7 +307,7 @@ int dp_env_create(const dp_grid_geom *g, int Tg, const float *grid, const float 
     DP_CUDA(cudaMalloc(&e->ws.partial, MAX_PARTIALS * sizeof(double)));
     DP_CUDA(cudaMalloc(&e->ws.partial_max, MAX_PARTIALS * sizeof(float)));
     dim3 blk(32, 8), grd((unsigned)((cells + 31) / 32), (unsigned)((Tg + 31) / 32));
-    env_pack_kernel<<<grd, blk>>>(d_in[0], d_in[1], d_in[2], g->gx, g->gy, Tg, e->d_table);
+    env_pack_kernel<<<grd, blk>>>(d_in[0], d_in[1], d_in[2], g->gx, g->gy, Tg, make_geom(*g), e->d_table);
     DP_CUDA(cudaGetLastError());
     DP_CUDA(cudaDeviceSynchronize());
     for (int i = 0; i < 3; ++i)

@@ -56,7 +56,7 @@ struct dp_env {
     int device = 0;
     dp_grid_geom geom;
     int Tg = 0;
-    float4 *d_table = nullptr;  // [Tg][gx][gy] {p, gradX, gradY, 0}
+    float4 *d_table = nullptr;  // [Tg][gx][gy] {p, des_pos_x, des_pos_y, active} (cost.cu env_pack_kernel)
 };
 
 // ---- error plumbing ---------------------------------------------------------------------------------------
@@ -218,17 +218,14 @@ struct DpEval {
     bool active;
 };
 
-// the terms of one evaluation from the gathered table entry e = {p, gradX, gradY, 0} of the (clamped) cell (ix, iy)
-__device__ __forceinline__ DpEval dp_cost_term_f(const float4 e, const DpGeom &q, float fx, float fy, float x, float y, float rho,
-                                                 bool has_rho) {
+// the terms of one evaluation from the gathered table entry e = {p, des_pos_x, des_pos_y, active} of the (clamped) cell: the
+// desired position (gridpos + 100 * grad through gridpos2pos, MotionPlanner.py:215-217) is a property of the cell and comes
+// precomputed from dp_env_create; what is left per sample is the squared distance and the weighting (:218-222), each op
+// rounded like torch
+__device__ __forceinline__ DpEval dp_cost_term(const float4 e, float x, float y, float rho, bool has_rho) {
     DpEval r;
-    r.active = (e.y != 0.0f) || (e.z != 0.0f);  // :213-214
-    // des_gridpos = gridpos + 100 * grad ; gridpos2pos ; squared distance (:215-218), each op rounded like torch
-    const float dgx = __fadd_rn(fx, __fmul_rn(100.0f, e.y));
-    const float dgy = __fadd_rn(fy, __fmul_rn(100.0f, e.z));
-    const float dpx = dp_pos<false>(dgx, q.x_lo, q.x_rng, q.gxm1, q.r_gxm1);
-    const float dpy = dp_pos<false>(dgy, q.y_lo, q.y_rng, q.gym1, q.r_gym1);
-    const float ex = __fsub_rn(dpx, x), ey = __fsub_rn(dpy, y);
+    r.active = e.w != 0.0f;  // :213-214
+    const float ex = __fsub_rn(e.y, x), ey = __fsub_rn(e.z, y);
     const float sq = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
     const float w = has_rho ? __fmul_rn(rho, e.x) : e.x;
     r.term = r.active ? __fmul_rn(w, sq) : 0.0f;
@@ -238,17 +235,12 @@ __device__ __forceinline__ DpEval dp_cost_term_f(const float4 e, const DpGeom &q
     return r;
 }
 
-__device__ __forceinline__ DpEval dp_cost_term(const float4 e, const DpGeom &q, int ix, int iy, float x, float y, float rho,
-                                               bool has_rho) {
-    return dp_cost_term_f(e, q, __int2float_rn(ix), __int2float_rn(iy), x, y, rho, has_rho);
-}
-
 __device__ __forceinline__ DpEval dp_cost_eval(const float4 *__restrict__ table, const DpGeom &q, int t, float x, float y, float rho,
                                                bool has_rho) {
     int ix, iy;
     float fx, fy;
     dp_cell_clamped(x, q.x_lo, q.x_rng, q.r_x_rng, q.gxm1, q.gxm1, ix, fx);  // clamp to [0, G-1] (:208-209)
     dp_cell_clamped(y, q.y_lo, q.y_rng, q.r_y_rng, q.gym1, q.gym1, iy, fy);
-    const float4 e = __ldg(table + ((size_t)t * q.gx + ix) * q.gy + iy);  // {p, gradX, gradY, 0}
-    return dp_cost_term_f(e, q, fx, fy, x, y, rho, has_rho);
+    const float4 e = __ldg(table + ((size_t)t * q.gx + ix) * q.gy + iy);  // {p, des_pos_x, des_pos_y, active}
+    return dp_cost_term(e, x, y, rho, has_rho);
 }
