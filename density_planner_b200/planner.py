@@ -79,10 +79,10 @@ class DensityNN:
             backend = "torch"  # the kernel mirrors the reference's default (ReLU); a tanh model keeps the batched torch pass
         self.backend = backend
         if backend == "kernel":
+            if not torch.cuda.is_available():
+                raise _lib.DensityPlannerError("DensityNN(backend='kernel') needs a B200; there is no CPU fallback "
+                                               "(backend='torch' is the CPU cross-check formulation)")
             if device is None or torch.device(device).type != "cuda":
-                if not torch.cuda.is_available():
-                    raise _lib.DensityPlannerError("DensityNN(backend='kernel') needs a B200; there is no CPU fallback "
-                                                   "(backend='torch' is the CPU cross-check formulation)")
                 device = torch.device("cuda", torch.cuda.current_device())
             dev = torch.device(device)
             if dev.index is None:

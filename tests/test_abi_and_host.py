@@ -167,3 +167,15 @@ def test_density_nn_batched_matches_reference_golden():
     gup_int = gu.reshape(1, 2, 10, 100).sum(axis=3)
     total = up.grad.numpy() + gup_int
     assert np.abs(total - g["gup"]).max() < 2e-3 * np.abs(g["gup"]).max()
+
+
+def test_density_nn_kernel_backend_fails_loudly_without_gpu():
+    """The product route of the density-NN branch is the fused CUDA kernel: without a GPU it raises, it does not fall back."""
+    import torch
+    import density_planner_b200 as dp
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the kernel backend is exercised by tests/test_gpu_planner_terms.py")
+    with pytest.raises(dp.DensityPlannerError):
+        dp.DensityNN()
+    with pytest.raises(dp.DensityPlannerError):
+        dp.DensityNN(device="cuda")
