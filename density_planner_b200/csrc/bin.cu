@@ -556,7 +556,7 @@ __global__ void normalize_apply_kernel(const float *__restrict__ rholog, const f
 
 }  // namespace
 
-// tuning / A-B knobs (read once): DP_BIN_THREADS = 768 (default, 40 registers per thread, two blocks per SM), 1024 (32 registers) or 512 (64 registers),
+// tuning / A-B knobs (read once): DP_BIN_THREADS = 768 (default, 40 registers per thread, two blocks per SM), 640 (48 registers), 1024 (32 registers) or 512 (64 registers),
 // DP_BIN_AGG = 0 (never aggregate), 1 (always), 2 (default: decided per block from a probe)
 static int bin_waves() {  // DP_BIN_BLOCKS_PER_SM: target number of blocks per SM over all slices (default 8; measured at the config-3 size: 2 -> 0.30 ms, 4 -> 0.25 ms, 8 -> 0.23 ms)
     static int s_w = 0;
@@ -578,7 +578,7 @@ static void bin_knobs(int &threads, int &agg) {
     static int s_threads = 0, s_agg = 2;
     if (!s_threads) {
         const char *e = getenv("DP_BIN_THREADS");
-        s_threads = (e && atoi(e) == 512) ? 512 : (e && atoi(e) == 1024) ? 1024 : 768;
+        s_threads = (e && atoi(e) == 512) ? 512 : (e && atoi(e) == 1024) ? 1024 : (e && atoi(e) == 640) ? 640 : 768;
         const char *g = getenv("DP_BIN_AGG");
         if (g) s_agg = atoi(g) < 0 ? 0 : (atoi(g) > 2 ? 2 : atoi(g));
     }
@@ -651,6 +651,10 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
     }
     int NT, agg;
     bin_knobs(NT, agg);
+    // the variant with the occupancy dot product carries more state per thread: at 768 threads (40 registers) ptxas
+    // rematerialises constants per sample; 640 threads (48 registers) measured 0.243 against 0.263 ms, while the plain
+    // binning prefers 768 (0.221 against 0.229 ms) -- profiles/r02_k3_threads.txt.  DP_BIN_THREADS overrides both.
+    if (occ_dot && !getenv("DP_BIN_THREADS")) NT = 640;
     BinArgs a;
     memset(&a, 0, sizeof(a));
     a.mode = spec->mode;
@@ -705,6 +709,7 @@ static int bin2d_launch(const dp_bin_spec *spec, const dp_env *env, const float 
                      sx_t % 4 == 0 && (!w || sw_t % 4 == 0);
     const dim3 grid((unsigned)B, (unsigned)Ts);
     const int rc = NT == 512   ? bin2d_dispatch<512>(a, vec, fused, grid, stream)
+                   : NT == 640 ? bin2d_dispatch<640>(a, vec, fused, grid, stream)
                    : NT == 768 ? bin2d_dispatch<768>(a, vec, fused, grid, stream)
                                : bin2d_dispatch<1024>(a, vec, fused, grid, stream);
     if (rc) return rc;
