@@ -375,7 +375,7 @@ int dp_cost_coll(const dp_env *e, const float *x, const float *y, int64_t sx_n, 
             static int s_minb = 0, s_waves = 0;  // A/B knobs: resident blocks per SM of the forward kernel, waves over all slices
             if (!s_minb) {
                 const char *me = getenv("DP_COST_FWD_MINB");
-                s_minb = (me && (atoi(me) == 6 || atoi(me) == 8)) ? atoi(me) : 4;
+                s_minb = (me && (atoi(me) == 4 || atoi(me) == 6 || atoi(me) == 8)) ? atoi(me) : 5;
                 const char *we = getenv("DP_COST_WAVES");
                 s_waves = (we && atoi(we) >= 1 && atoi(we) <= 16) ? atoi(we) : 4;
             }
@@ -397,6 +397,8 @@ int dp_cost_coll(const dp_env *e, const float *x, const float *y, int64_t sx_n, 
                 cost_vec4_kernel<false, 4><<<grid, CB, 0, stream>>>(a);
             else if (minb == 8)
                 cost_vec4_kernel<false, 8><<<grid, CB, 0, stream>>>(a);
+            else if (minb == 5)  // forward default: 48 registers, 0.219 ms against 0.226 ms at four blocks (profiles/r02_cost_knobs.txt)
+                cost_vec4_kernel<false, 5><<<grid, CB, 0, stream>>>(a);
             else
                 cost_vec4_kernel<false, 6><<<grid, CB, 0, stream>>>(a);
         }
