@@ -10,7 +10,17 @@ import torch
 
 
 def compute_data(iteration_number, samples_x, system, args, samples_t=None, save=True, plot=True):
-    """Generate `iteration_number[0]` files of `iteration_number[1]` trajectories with `samples_x` samples each."""
+    """Generate `iteration_number[0]` files of `iteration_number[1]` trajectories with `samples_x` samples each.
+
+    The rollout consumes no random numbers and the number of time points follows from the reference alone, so drawing all
+    references / initial errors / time indices of a file first (in the reference's order) and rolling them out in ONE launch
+    (`compute_data_batched`: references of at most 64 samples share the 128-lane tiles) gives the same result dictionaries as
+    the reference's trajectory-by-trajectory loop.  That is what this entry does unless the system overrides
+    `get_valid_trajectories` (then the loop below calls it per trajectory, as the reference does)."""
+    from .systems import ControlAffineSystem
+    if not plot and getattr(type(system), "get_valid_trajectories", None) is ControlAffineSystem.get_valid_trajectories \
+            and hasattr(system, "compute_density_batch"):
+        return compute_data_batched(iteration_number, samples_x, system, args, samples_t=samples_t, save=save)
     results_all = []
     for _ in range(iteration_number[0]):
         for _ in range(iteration_number[1]):
@@ -66,8 +76,14 @@ def compute_data_batched(iteration_number, samples_x, system, args, samples_t=No
             else:
                 indizes = torch.arange(0, t.shape[0])
             pending.append((up, uref_traj, xref_traj, xe0, t, indizes))
-        outs = system.compute_density_batch([p[3] for p in pending], [p[2] for p in pending], [p[1] for p in pending],
-                                            args.dt_sim, cutting=True, log_density=True, compute_density=True)
+        # one launch per file; files whose stored trajectories would exceed ~8 GB are rolled out in several launches
+        per_ref = 24 * int(samples_x) * max(int(p[2].shape[2]) for p in pending) if pending else 1
+        group = max(1, int(8e9 // max(per_ref, 1)))
+        outs = []
+        for g0 in range(0, len(pending), group):
+            part = pending[g0:g0 + group]
+            outs += system.compute_density_batch([p[3] for p in part], [p[2] for p in part], [p[1] for p in part],
+                                                 args.dt_sim, cutting=True, log_density=True, compute_density=True)
         for (up, uref_traj, xref_traj, xe0, t, indizes), (xe_traj, rho_traj) in zip(pending, outs):
             xe_s, rho_s = xe_traj[:, :, ::k], rho_traj[:, :, ::k]
             results_all.append({

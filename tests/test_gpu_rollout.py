@@ -250,10 +250,24 @@ def _check_rawdata_against_golden(car, args, res, g):
 
 
 def test_compute_data_matches_reference_golden(dp, car, args):
-    """data_generation/compute_rawdata.py:9 with seed 5: same references, same samples, same time indices."""
+    """data_generation/compute_rawdata.py:9 with seed 5: same references, same samples, same time indices.  `compute_data`
+    rolls a file out in one packed launch; a system that overrides get_valid_trajectories gets the reference's
+    trajectory-by-trajectory loop (one launch each) -- both reproduce the golden."""
     g = golden("compute_data.npz")
+
+    class LoopCar(type(car)):  # forces the per-trajectory loop of compute_data
+        def get_valid_trajectories(self, *a, **k):
+            return super().get_valid_trajectories(*a, **k)
+
+    loop_car = LoopCar(args)
+    torch.manual_seed(5)
+    res_loop = dp.compute_data([1, 2], 20, loop_car, args, samples_t=10, save=False, plot=False)
     torch.manual_seed(5)
     res = dp.compute_data([1, 2], 20, car, args, samples_t=10, save=False, plot=False)
+    assert len(res_loop) == len(res) == 2
+    for a, b in zip(res_loop, res):
+        for k in a:
+            assert bool((torch.as_tensor(a[k]) == torch.as_tensor(b[k])).all()), k   # packed launch == single launches, bit for bit
     assert len(res) == 2
     for i, r in enumerate(res):
         assert (r["u_params"].numpy() == g["r%d_u_params" % i]).all()
