@@ -68,7 +68,7 @@ _SIGNATURES = {
     "dp_pipeline_finalize": (_int, [_vp, _vp, _vp, _vp]),
     "dp_pipeline_copy_slices": (_int, [_vp, _vp, _vp, _vp]),
     "dp_rollout_fused": (_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp, _vp]),
-    "dp_dnn_create": (_int, [_vp, _vp, _vp, _int, _int, ctypes.POINTER(_vp)]),
+    "dp_dnn_create": (_int, [_vp, _vp, _vp, _int, _int, _int, ctypes.POINTER(_vp)]),
     "dp_dnn_destroy": (None, [_vp]),
     "dp_dnn_mask_words": (_int, [_vp, ctypes.POINTER(_int)]),
     "dp_dnn_forward": (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),

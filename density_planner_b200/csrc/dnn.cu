@@ -33,7 +33,8 @@ constexpr int D_LAYER = 2 * D_IMG;             // hi + lo
 constexpr uint32_t D_LBO = 128;                // K-adjacent core matrices (8 rows x 16 bytes) are contiguous
 constexpr uint32_t D_SBO = (DW / 8) * 128;     // next 8-row group
 constexpr int D_MAX_LAYERS = 8;
-constexpr int D_MASK_WORDS = DW / 32;          // ReLU sign bits per layer and row
+constexpr int D_MASK_WORDS = DW / 32;          // ReLU: sign bits per layer and row
+constexpr int D_TANH_WORDS = DW / 2;           // tanh: the activations themselves as fp16 pairs (the gate is 1 - h^2)
 constexpr int D_OFF_BIAS = 2 * D_LAYER;        // float [8][160]
 constexpr int D_OFF_BAR = D_OFF_BIAS + D_MAX_LAYERS * DW * 4;
 constexpr int D_SMEM = D_OFF_BAR + 64;
@@ -45,7 +46,7 @@ struct DnnParams {
     const float *bias;         // [n_layers][DW], forward only
     const float *in;           // [rows][in_w]
     float *out;                // [rows][out_w]
-    uint32_t *masks;           // [rows][n_layers - 1][D_MASK_WORDS]: written by the forward pass, read by the backward pass
+    uint32_t *masks;           // [rows][n_layers - 1][D_MASK_WORDS or D_TANH_WORDS]: written by forward, read by backward
     long long rows;
     int n_layers, in_w, out_w;
     int nk[D_MAX_LAYERS];      // K steps (of 16) per pass
@@ -53,7 +54,7 @@ struct DnnParams {
 
 __device__ __forceinline__ float2 f2_of(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
-template <bool BWD>
+template <bool BWD, bool TANH>
 __global__ void __launch_bounds__(128, 1) dnn_kernel(DnnParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(128, 1) dnn_kernel(DnnParams p) {
             fence_after();
             const bool last = pass + 1 == p.n_layers;
             const float2 inv = make_float2(INV_WSCALE, INV_WSCALE);
-            if (!last) {
+            if (!last && !TANH) {
                 // hidden layer: forward = scale, bias, ReLU (sign bits kept), backward = scale, ReLU mask of the layer below;
                 // either way the result becomes the next pass's operand
                 const int hid = BWD ? n_hidden - 1 - pass : pass;
@@ -187,6 +188,43 @@ __global__ void __launch_bounds__(128, 1) dnn_kernel(DnnParams p) {
 #pragma unroll
                     for (int w = 0; w < D_MASK_WORDS; ++w) p.masks[(row * n_hidden + hid) * D_MASK_WORDS + w] = mw[w];
                 }
+            } else if (!last) {
+                // tanh hidden layer (the reference's other activation, density_training/utils.py:16-17): forward keeps the
+                // activations as fp16 pairs -- the hi half of the operand split -- and the backward pass forms the gate 1 - h^2
+                // from them (11 bits on the gate: the gradient contract is 2e-3)
+                const int hid = BWD ? n_hidden - 1 - pass : pass;
+                uint32_t *hrow = p.masks ? p.masks + (row * n_hidden + hid) * D_TANH_WORDS : nullptr;
+#pragma unroll
+                for (int c = 0; c < DW / 16; ++c) {
+                    uint32_t d[16], av[16], hw[8];
+                    ld16(ACC + lane_off + 16 * c, d);
+                    if (BWD) {
+#pragma unroll
+                        for (int pq = 0; pq < 8; ++pq) hw[pq] = (valid && hrow) ? __ldg(hrow + 8 * c + pq) : 0u;
+                    }
+                    wait_ld();
+#pragma unroll
+                    for (int pq = 0; pq < 8; ++pq) {
+                        float2 y;
+                        if (!BWD) {
+                            const float2 b = *reinterpret_cast<const float2 *>(sBias + pass * DW + 16 * c + 2 * pq);
+                            y = __ffma2_rn(f2_of(d[2 * pq], d[2 * pq + 1]), inv, b);
+                            y.x = tanh_fast(y.x);
+                            y.y = tanh_fast(y.y);
+                        } else {
+                            const float2 h = __half22float2(bits_h2(hw[pq]));
+                            y = __fmul2_rn(f2_of(d[2 * pq], d[2 * pq + 1]), inv);
+                            y.x *= fmaf(-h.x, h.x, 1.0f);
+                            y.y *= fmaf(-h.y, h.y, 1.0f);
+                        }
+                        split_h2_mixed(y, av[pq], av[8 + pq]);
+                    }
+                    if (!BWD && valid && hrow) {
+#pragma unroll
+                        for (int pq = 0; pq < 8; ++pq) hrow[8 * c + pq] = av[pq];
+                    }
+                    st16(OPER + lane_off + 16 * c, av);
+                }
             } else {
                 // output layer: forward adds the bias, backward is the plain product; the first out_w columns go to global
                 for (int c = 0; 16 * c < p.out_w; ++c) {
@@ -223,6 +261,7 @@ inline size_t dnn_canon(int n, int k) { return ((size_t)(n / 8) * (DW / 8) + (k 
 struct dp_dnn {
     int device = 0, num_sms = 0;
     int n_layers = 0;
+    int tanh_act = 0;  // 0: ReLU, 1: tanh
     int dims[D_MAX_LAYERS + 1] = {};
     unsigned char *d_fwd = nullptr;  // [n_layers] images B[n = output feature][k = input feature] of layer l
     unsigned char *d_bwd = nullptr;  // [n_layers] images B[n = input feature][k = output feature] of layer n_layers-1-pass
@@ -231,9 +270,10 @@ struct dp_dnn {
 
 extern "C" {
 
-int dp_dnn_create(const float *const *weights, const float *const *biases, const int *dims, int n_layers, int device,
-                  dp_dnn **out) {
+int dp_dnn_create(const float *const *weights, const float *const *biases, const int *dims, int n_layers, int activation,
+                  int device, dp_dnn **out) {
     DP_REQUIRE(weights && biases && dims && out, "dp_dnn_create: null argument");
+    DP_REQUIRE(activation == 0 || activation == 1, "dp_dnn_create: activation is 0 (ReLU) or 1 (tanh)");
     DP_REQUIRE(n_layers >= 1 && n_layers <= D_MAX_LAYERS, "dp_dnn_create: 1..%d layers supported (got %d)", D_MAX_LAYERS, n_layers);
     for (int l = 0; l <= n_layers; ++l)
         DP_REQUIRE(dims[l] >= 1 && dims[l] <= DW, "dp_dnn_create: layer widths up to %d supported (dims[%d] = %d)", DW, l, dims[l]);
@@ -262,6 +302,7 @@ int dp_dnn_create(const float *const *weights, const float *const *biases, const
     dp_dnn *h = new dp_dnn();
     h->device = device;
     h->n_layers = n_layers;
+    h->tanh_act = activation;
     for (int l = 0; l <= n_layers; ++l) h->dims[l] = dims[l];
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || cudaMalloc(&h->d_fwd, fwd.size()) || cudaMalloc(&h->d_bwd, bwd.size()) ||
@@ -273,8 +314,10 @@ int dp_dnn_create(const float *const *weights, const float *const *biases, const
         return 1;
     }
     h->num_sms = prop.multiProcessorCount;
-    DP_CUDA(cudaFuncSetAttribute(dnn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
-    DP_CUDA(cudaFuncSetAttribute(dnn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
+    DP_CUDA(cudaFuncSetAttribute(dnn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
+    DP_CUDA(cudaFuncSetAttribute(dnn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
+    DP_CUDA(cudaFuncSetAttribute(dnn_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
+    DP_CUDA(cudaFuncSetAttribute(dnn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
     *out = h;
     return 0;
 }
@@ -290,7 +333,7 @@ void dp_dnn_destroy(dp_dnn *h) {
 
 int dp_dnn_mask_words(const dp_dnn *h, int *words_per_row) {
     DP_REQUIRE(h && words_per_row, "dp_dnn_mask_words: null argument");
-    *words_per_row = (h->n_layers - 1) * D_MASK_WORDS;
+    *words_per_row = (h->n_layers - 1) * (h->tanh_act ? D_TANH_WORDS : D_MASK_WORDS);
     return 0;
 }
 
@@ -305,7 +348,10 @@ int dp_dnn_forward(const dp_dnn *h, const float *x, int64_t rows, float *y, uint
     for (int l = 0; l < h->n_layers; ++l) p.nk[l] = (h->dims[l] + 15) / 16;
     const long long ntiles = (rows + 127) / 128;
     const int grid = (int)(ntiles < h->num_sms ? ntiles : h->num_sms);
-    dnn_kernel<false><<<grid, 128, D_SMEM, (cudaStream_t)stream>>>(p);
+    if (h->tanh_act)
+        dnn_kernel<false, true><<<grid, 128, D_SMEM, (cudaStream_t)stream>>>(p);
+    else
+        dnn_kernel<false, false><<<grid, 128, D_SMEM, (cudaStream_t)stream>>>(p);
     DP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -321,7 +367,10 @@ int dp_dnn_backward(const dp_dnn *h, const float *gy, const uint32_t *masks, int
     for (int q = 0; q < h->n_layers; ++q) p.nk[q] = (h->dims[h->n_layers - q] + 15) / 16;  // pass q runs layer n_layers-1-q transposed
     const long long ntiles = (rows + 127) / 128;
     const int grid = (int)(ntiles < h->num_sms ? ntiles : h->num_sms);
-    dnn_kernel<true><<<grid, 128, D_SMEM, (cudaStream_t)stream>>>(p);
+    if (h->tanh_act)
+        dnn_kernel<true, true><<<grid, 128, D_SMEM, (cudaStream_t)stream>>>(p);
+    else
+        dnn_kernel<true, false><<<grid, 128, D_SMEM, (cudaStream_t)stream>>>(p);
     DP_CUDA(cudaGetLastError());
     return 0;
 }

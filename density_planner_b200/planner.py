@@ -56,7 +56,7 @@ class DensityNN:
     128-row tile on the SM, split-fp16 operands with fp32-level accuracy), differentiable w.r.t. the rows, i.e. w.r.t. `up` and
     `xe0` like the reference's branch.  It needs a B200 and raises without one -- there is no CPU fallback.
     backend "torch": the same batched formulation in plain torch (addmm) -- the cross-check the CPU tests replay against the
-    reference golden, and the route for the one configuration the kernel does not mirror (tanh activation)."""
+    reference golden."""
 
     def __init__(self, weights=None, device=None, activation="relu", backend="kernel"):
         import ctypes
@@ -75,8 +75,6 @@ class DensityNN:
         bn = [np.ascontiguousarray(np.asarray(z["linear_list.%d.bias" % i], dtype="float32")) for i in range(n_layers)]
         self.dims = [int(Wn[0].shape[1])] + [int(w.shape[0]) for w in Wn]
         self.handle, self.mask_words = None, 0
-        if backend == "kernel" and activation == "tanh":
-            backend = "torch"  # the kernel mirrors the reference's default (ReLU); a tanh model keeps the batched torch pass
         self.backend = backend
         if backend == "kernel":
             if not torch.cuda.is_available():
@@ -92,7 +90,8 @@ class DensityNN:
             bp = (ctypes.c_void_p * n_layers)(*[b.ctypes.data for b in bn])
             dims = (ctypes.c_int * (n_layers + 1))(*self.dims)
             h = ctypes.c_void_p()
-            _lib.check(L.dp_dnn_create(wp, bp, dims, n_layers, dev.index, ctypes.byref(h)), "dp_dnn_create")
+            _lib.check(L.dp_dnn_create(wp, bp, dims, n_layers, 1 if activation == "tanh" else 0, dev.index, ctypes.byref(h)),
+                       "dp_dnn_create")
             self.handle = h
             mw = ctypes.c_int()
             _lib.check(L.dp_dnn_mask_words(h, ctypes.byref(mw)), "dp_dnn_mask_words")

@@ -290,14 +290,16 @@ int dp_rollout_fused(dp_pipeline *p, const float *xe0, const float *rho0, const 
  * call run through the whole layer stack in ONE fused tcgen05 kernel (csrc/dnn.cu); the backward call returns the gradient
  * w.r.t. the input rows (the planner differentiates w.r.t. the input parameters, the weights are frozen).
  *   weights[l] host fp32 [dims[l+1]][dims[l]] (torch Linear.weight layout), biases[l] host fp32 [dims[l+1]],
- *   l = 0 .. n_layers-1, ReLU after every layer but the last; n_layers <= 8, every width <= 160.
+ *   l = 0 .. n_layers-1; activation 0 = ReLU, 1 = tanh (args.activation, density_training/utils.py:14-19) after every layer
+ *   but the last; n_layers <= 8, every width <= 160.
  *   x dev [rows][dims[0]] -> y dev [rows][dims[n_layers]]
- *   masks dev uint32 [rows][dp_dnn_mask_words()] or NULL: ReLU sign bits, written by forward, read by backward
+ *   masks dev uint32 [rows][dp_dnn_mask_words()] or NULL: what the backward pass needs of the forward pass (ReLU sign bits, or
+ *   the tanh activations as fp16 pairs), written by forward, read by backward
  *   gy dev [rows][dims[n_layers]] -> gx dev [rows][dims[0]]
  */
 typedef struct dp_dnn dp_dnn;
-int dp_dnn_create(const float *const *weights, const float *const *biases, const int *dims, int n_layers, int device,
-                  dp_dnn **out);
+int dp_dnn_create(const float *const *weights, const float *const *biases, const int *dims, int n_layers, int activation,
+                  int device, dp_dnn **out);
 void dp_dnn_destroy(dp_dnn *h);
 int dp_dnn_mask_words(const dp_dnn *h, int *words_per_row);
 int dp_dnn_forward(const dp_dnn *h, const float *x, int64_t rows, float *y, uint32_t *masks, void *stream);
